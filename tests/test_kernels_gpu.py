@@ -1,0 +1,348 @@
+"""Per-kernel numerics on the B200: every CUDA kernel (called through the C ABI) against a plain PyTorch fp32
+reference of the same op on the same fp16-rounded inputs.
+
+Tolerance (stated per SURVEY §7 "Numerics"): outputs are fp16 with fp32 accumulation, so the bound is a few fp16
+ulps of the output scale:  max|err| <= 3e-3 * max|ref| + 1e-3.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _close(out, ref, what, rel=3e-3, abs_=1e-3):
+    out = out.float()
+    ref = ref.float()
+    assert out.shape == ref.shape, f"{what}: shape {out.shape} vs {ref.shape}"
+    assert torch.isfinite(out).all(), f"{what}: non-finite output"
+    err = (out - ref).abs().max().item()
+    bound = rel * ref.abs().max().item() + abs_
+    assert err <= bound, f"{what}: max err {err:.4e} > bound {bound:.4e} (ref max {ref.abs().max().item():.3e})"
+    return err
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def _pack_conv_w(w):
+    """[Cout, Cin, KH, KW] -> [Cout, KH*KW*Cin] (tap-major, channel-minor), fp16."""
+    co, ci, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous().half()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from tooncrafter_b200 import ops as _ops
+    return _ops
+
+
+@pytest.mark.parametrize("rows,K,N", [(300, 320, 320), (4096, 1280, 1280), (128, 64, 16), (2560, 640, 160),
+                                       (77, 1024, 640), (1000, 512, 4)])
+def test_linear_bias_residual(ops, rows, K, N):
+    x = _rand(rows, K, seed=1).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=2).half()
+    bias = _rand(N, seed=3).float()
+    res = _rand(rows, N, seed=4).half()
+    out = torch.zeros(rows, N, dtype=torch.float16, device=DEV)
+    ops.linear(x, w, out, rows=rows, K=K, n_cols=N, bias=bias, res=res)
+    ref = x.float() @ w.float().t() + bias + res.float()
+    _close(out, ref, f"linear {rows}x{K}x{N}")
+
+
+def test_linear_strided_slices(ops):
+    """A read from / output written into channel slices of wider tensors (concat-by-construction)."""
+    rows, K, N = 640, 128, 192
+    xw = _rand(rows, 256, seed=5).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=6).half()
+    outw = torch.full((rows, 512), 7.0, dtype=torch.float16, device=DEV)
+    ops.linear(xw, w, outw, rows=rows, K=K, n_cols=N, ldx=256, ldc=512, a_offset=128, out_offset=64)
+    ref = xw[:, 128:256].float() @ w.float().t()
+    _close(outw[:, 64:64 + N], ref, "linear slices")
+    assert (outw[:, :64] == 7.0).all() and (outw[:, 64 + N:] == 7.0).all(), "wrote outside the slice"
+
+
+def test_linear_geglu(ops):
+    rows, K, inner = 1000, 320, 1280
+    x = _rand(rows, K, seed=7).half()
+    w = _rand(2 * inner, K, scale=K ** -0.5, seed=8).half()   # reference layout: [a ; gate]
+    b = _rand(2 * inner, seed=9).float()
+    BN = 256
+    hb = BN // 2
+    # pack per N tile: [a rows of tile | gate rows of tile]
+    wa, wg = w[:inner], w[inner:]
+    ba, bg = b[:inner], b[inner:]
+    wp = torch.cat([torch.cat([wa[i:i + hb], wg[i:i + hb]]) for i in range(0, inner, hb)]).contiguous()
+    bp = torch.cat([torch.cat([ba[i:i + hb], bg[i:i + hb]]) for i in range(0, inner, hb)]).contiguous()
+    out = torch.zeros(rows, inner, dtype=torch.float16, device=DEV)
+    ops.linear(x, wp, out, rows=rows, K=K, n_cols=2 * inner, bias=bp, geglu=True, block_n=BN)
+    h = x.float() @ w.float().t() + b
+    ref = h[:, :inner] * F.gelu(h[:, inner:])
+    _close(out, ref, "geglu")
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(4, 20, 32, 128, 192), (6, 5, 8, 256, 320), (2, 40, 64, 64, 320),
+                                             (3, 10, 16, 320, 4), (1, 16, 256, 128, 128)])
+def test_conv3x3(ops, N, H, W, Cin, Cout):
+    x = _rand(N, H, W, Cin, seed=11).half()            # channels-last
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=12)
+    bias = _rand(Cout, seed=13).float()
+    out = torch.zeros(N, H, W, Cout, dtype=torch.float16, device=DEV)
+    ops.conv_gemm(x, (N, H, W, Cin), (H * W * Cin, W * Cin, Cin), _pack_conv_w(w), ops.TAPS_3x3, out, (N, H, W),
+                  Cout, bias=bias)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), bias, padding=1).permute(0, 2, 3, 1)
+    _close(out, ref, f"conv3x3 {N}x{H}x{W} {Cin}->{Cout}")
+
+
+def test_conv3x3_emb_bias_and_skip(ops):
+    """ResBlock-style epilogue: + per-sample embedding vector (bias2) + residual."""
+    B, T, H, W, C = 2, 4, 10, 16, 128
+    N = B * T
+    x = _rand(N, H, W, C, seed=14).half()
+    w = _rand(C, C, 3, 3, scale=(9 * C) ** -0.5, seed=15)
+    bias = _rand(C, seed=16).float()
+    emb = _rand(B, C, seed=17).half()
+    res = _rand(N, H, W, C, seed=18).half()
+    out = torch.zeros(N, H, W, C, dtype=torch.float16, device=DEV)
+    ops.conv_gemm(x, (N, H, W, C), (H * W * C, W * C, C), _pack_conv_w(w), ops.TAPS_3x3, out, (N, H, W), C,
+                  bias=bias, bias2=emb, bias2_rows_per=T * H * W, res=res)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), bias, padding=1).permute(0, 2, 3, 1)
+    ref = ref + emb.float().repeat_interleave(T, 0)[:, None, None, :] + res.float()
+    _close(out, ref, "conv3x3 + emb + skip")
+
+
+@pytest.mark.parametrize("B,T,H,W,C", [(2, 16, 5, 8, 128), (1, 16, 20, 32, 64), (1, 14, 10, 16, 128)])
+def test_temporal_conv(ops, B, T, H, W, C):
+    """(3,1,1) Conv3d == 3-tap conv over T on the [B][T][HW][C] view."""
+    x = _rand(B, T, H * W, C, seed=21).half()
+    w = _rand(C, C, 3, 1, 1, scale=(3 * C) ** -0.5, seed=22)
+    bias = _rand(C, seed=23).float()
+    res = _rand(B, T, H * W, C, seed=24).half()
+    out = torch.zeros_like(x)
+    wp = w[:, :, :, 0, 0].permute(0, 2, 1).reshape(C, 3 * C).contiguous().half()
+    ops.conv_gemm(x, (B, T, H * W, C), (T * H * W * C, H * W * C, C), wp, ops.TAPS_T3, out, (B, T, H * W), C,
+                  bias=bias, res=res, acc_scale=0.5)
+    xr = x.float().reshape(B, T, H, W, C).permute(0, 4, 1, 2, 3)
+    ref = F.conv3d(xr, w.half().float(), bias, padding=(1, 0, 0)).permute(0, 2, 3, 4, 1).reshape(B, T, H * W, C)
+    ref = ref * 0.5 + res.float()
+    _close(out, ref, "temporal conv")
+
+
+def test_conv3x3_stride2(ops):
+    N, H, W, C, Cout = 4, 20, 32, 64, 128
+    x = _rand(N, H, W, C, seed=31).half()
+    w = _rand(Cout, C, 3, 3, scale=(9 * C) ** -0.5, seed=32)
+    bias = _rand(Cout, seed=33).float()
+    ph = torch.zeros(4, N, H // 2, W // 2, C, dtype=torch.float16, device=DEV)
+    ops.phase_split2(x, ph, N=N, H=H, W=W, C_=C)
+    out = torch.zeros(N, H // 2, W // 2, Cout, dtype=torch.float16, device=DEV)
+    H2, W2 = H // 2, W // 2
+    ops.conv_gemm(ph, (4 * N, H2, W2, C), (H2 * W2 * C, W2 * C, C), _pack_conv_w(w), ops.taps_3x3_stride2(N), out,
+                  (N, H2, W2), Cout, bias=bias)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), bias, stride=2, padding=1).permute(0, 2, 3, 1)
+    _close(out, ref, "conv3x3 stride 2")
+
+
+@pytest.mark.parametrize("frames,fps,hw,C,silu,eps", [(8, 1, 160, 320, True, 1e-5), (8, 4, 40, 1280, True, 1e-5),
+                                                      (4, 1, 2560, 640, False, 1e-6), (16, 16, 640, 128, True, 1e-5),
+                                                      (2, 1, 20480, 256, True, 1e-6), (4, 2, 64, 1920, True, 1e-5)])
+def test_groupnorm(ops, frames, fps, hw, C, silu, eps):
+    x = (_rand(frames, hw, C, seed=41) * 1.5 + 0.3).half()
+    gamma = (_rand(C, seed=42) * 0.2 + 1.0).float()
+    beta = (_rand(C, seed=43) * 0.2).float()
+    y = torch.zeros_like(x)
+    ops.groupnorm(x, y, gamma, beta, frames=frames, frames_per_stat=fps, hw=hw, C=C, eps=eps, silu=silu)
+    xr = x.float().reshape(frames // fps, fps * hw, C).permute(0, 2, 1)   # (n_stat, C, L)
+    ref = F.group_norm(xr, 32, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1).reshape(frames, hw, C)
+    _close(y, ref, "groupnorm")
+
+
+@pytest.mark.parametrize("rows,C", [(1000, 320), (333, 640), (77, 1280), (64, 512)])
+def test_layernorm(ops, rows, C):
+    x = (_rand(rows, C, seed=51) * 2 + 0.5).half()
+    gamma = (_rand(C, seed=52) * 0.2 + 1.0).float()
+    beta = (_rand(C, seed=53) * 0.2).float()
+    y = torch.zeros_like(x)
+    ops.layernorm(x, y, gamma, beta, rows=rows, C=C)
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    _close(y, ref, "layernorm")
+
+
+def _sdpa_ref(q, k, v, heads):
+    """q [B, Lq, h*64], k/v [B, Lk, h*64] fp16 -> fp32 attention output [B, Lq, h*64]."""
+    B, Lq, _ = q.shape
+    qh = q.float().reshape(B, Lq, heads, 64).transpose(1, 2)
+    kh = k.float().reshape(B, -1, heads, 64).transpose(1, 2)
+    vh = v.float().reshape(B, -1, heads, 64).transpose(1, 2)
+    s = (qh @ kh.transpose(-1, -2)) * 64 ** -0.5
+    o = s.softmax(-1) @ vh
+    return o.transpose(1, 2).reshape(B, Lq, heads * 64)
+
+
+@pytest.mark.parametrize("B,L,heads", [(2, 300, 2), (3, 128, 1), (2, 2560, 5), (4, 40, 3), (1, 640, 10)])
+def test_attention_self(ops, B, L, heads):
+    C = heads * 64
+    q = _rand(B, L, C, seed=61).half()
+    k = _rand(B, L, C, seed=62).half()
+    v = _rand(B, L, C, seed=63).half()
+    out = torch.zeros_like(q)
+    ops.attention(q, [dict(k=k, v=v, ldk=C, ldv=C, Lk=L)], out, q_batches=B, Lq=L, heads=heads, scale=64 ** -0.5,
+                  ldq=C, ldo=C)
+    _close(out, _sdpa_ref(q, k, v, heads), f"self attention L={L}")
+
+
+def test_attention_fused_qkv_layout(ops):
+    """q/k/v as column slices of one [tokens][3C] projection output."""
+    B, L, heads = 2, 200, 2
+    C = heads * 64
+    qkv = _rand(B, L, 3 * C, seed=64).half()
+    out = torch.zeros(B, L, C, dtype=torch.float16, device=DEV)
+    ops.attention(qkv, [dict(k=qkv, v=qkv, ldk=3 * C, ldv=3 * C, Lk=L, k_offset=C, v_offset=2 * C)], out,
+                  q_batches=B, Lq=L, heads=heads, scale=64 ** -0.5, ldq=3 * C, ldo=C)
+    ref = _sdpa_ref(qkv[..., :C].contiguous(), qkv[..., C:2 * C].contiguous(), qkv[..., 2 * C:].contiguous(), heads)
+    _close(out, ref, "attention on fused qkv")
+
+
+def test_attention_cross_text_plus_image(ops):
+    """Two-segment cross attention: text K/V shared by the T frames of a sample, image K/V per frame."""
+    Bs, T, L, heads = 2, 4, 160, 5
+    C = heads * 64
+    N = Bs * T
+    q = _rand(N, L, C, seed=65).half()
+    kt = _rand(Bs, 77, C, seed=66).half()
+    vt = _rand(Bs, 77, C, seed=67).half()
+    ki = _rand(N, 16, C, seed=68).half()
+    vi = _rand(N, 16, C, seed=69).half()
+    out = torch.zeros_like(q)
+    ops.attention(q, [dict(k=kt, v=vt, ldk=C, ldv=C, Lk=77, kv_div=T), dict(k=ki, v=vi, ldk=C, ldv=C, Lk=16)], out,
+                  q_batches=N, Lq=L, heads=heads, scale=64 ** -0.5, ldq=C, ldo=C)
+    ref = _sdpa_ref(q, kt.repeat_interleave(T, 0), vt.repeat_interleave(T, 0), heads) + _sdpa_ref(q, ki, vi, heads)
+    _close(out, ref, "cross attention text+image")
+
+
+def test_attention_long_kv(ops):
+    """VAE dual-reference style: Lq != Lk, all query batches share kv batch 0."""
+    N, Lq, Lk, heads = 3, 512, 1100, 2
+    C = heads * 64
+    q = _rand(N, Lq, C, seed=70).half()
+    k = _rand(1, Lk, C, seed=71).half()
+    v = _rand(1, Lk, C, seed=72).half()
+    out = torch.zeros_like(q)
+    ops.attention(q, [dict(k=k, v=v, ldk=C, ldv=C, Lk=Lk, kv_div=N)], out, q_batches=N, Lq=Lq, heads=heads,
+                  scale=64 ** -0.5, ldq=C, ldo=C)
+    _close(out, _sdpa_ref(q, k.expand(N, -1, -1), v.expand(N, -1, -1), heads), "attention long kv")
+
+
+@pytest.mark.parametrize("B,T,P,heads", [(2, 16, 40, 5), (1, 16, 640, 10), (1, 14, 33, 2), (1, 20, 10, 1)])
+def test_temporal_attention(ops, B, T, P, heads):
+    C = heads * 64
+    qkv = _rand(B, T, P, 3 * C, seed=81).half()
+    out = torch.zeros(B, T, P, C, dtype=torch.float16, device=DEV)
+    ops.temporal_attention(qkv, qkv, qkv, out, ld=3 * C, ldo=C, B=B, T=T, P=P, heads=heads, scale=64 ** -0.5,
+                           k_offset=C, v_offset=2 * C)
+    x = qkv.float().permute(0, 2, 1, 3).reshape(B * P, T, 3 * C)   # (b p) t c
+    ref = _sdpa_ref(x[..., :C].half(), x[..., C:2 * C].half(), x[..., 2 * C:].half(), heads)
+    ref = ref.reshape(B, P, T, C).permute(0, 2, 1, 3)
+    _close(out, ref, "temporal attention")
+
+
+def test_softmax_rows(ops):
+    s = _rand(300, 2560, scale=3.0, seed=85).half()
+    ref = (s.float() * 0.125).softmax(-1)
+    ops.softmax_rows(s, rows=300, cols=2560, scale=0.125)
+    _close(s, ref, "softmax rows", rel=2e-3, abs_=1e-5)
+
+
+def test_layout_and_elementwise(ops):
+    B, Cc, T, H, W = 2, 4, 3, 6, 8
+    x = _rand(B, Cc, T, H, W, seed=91)
+    y = torch.zeros(B, T, H, W, 64, dtype=torch.float16, device=DEV)
+    ops.ncthw_to_cl(x, y, B=B, C_=Cc, T=T, H=H, W=W, Cpad=64, coff=4, scale=0.5)
+    ref = (x * 0.5).permute(0, 2, 3, 4, 1)
+    _close(y[..., 4:8], ref, "ncthw_to_cl")
+    assert (y[..., :4] == 0).all() and (y[..., 8:] == 0).all()
+    back = torch.zeros(B, Cc, T, H, W, dtype=torch.float32, device=DEV)
+    ops.cl_to_ncthw(y, back, B=B, C_=Cc, T=T, H=H, W=W, ldx=64, x_offset=4)
+    _close(back, (x * 0.5).half().float(), "cl_to_ncthw", rel=0, abs_=0)
+
+    a = _rand(3, 5, 7, 64, seed=92).half()
+    up = torch.zeros(3, 10, 14, 64, dtype=torch.float16, device=DEV)
+    ops.upsample2x(a, up, N=3, H=5, W=7, C_=64)
+    ref = F.interpolate(a.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    _close(up, ref, "upsample2x", rel=0, abs_=0)
+
+    src = _rand(100, 128, seed=93).half()
+    dst = torch.zeros(100, 256, dtype=torch.float16, device=DEV)
+    ops.copy2d(src, dst, rows=100, cols=128, lds=128, ldd=256, dst_offset=64)
+    assert torch.equal(dst[:, 64:192], src) and (dst[:, :64] == 0).all()
+    ops.add2d(src, dst, rows=100, cols=128, ldx=128, ldy=256, y_offset=64)
+    _close(dst[:, 64:192], 2 * src.float(), "add2d", rel=1e-3, abs_=0)
+
+
+def test_time_embed_and_small_linear(ops):
+    B, dim, hidden = 2, 320, 1280
+    t = torch.tensor([999.0, 19.0], device=DEV)
+    w1 = _rand(hidden, dim, scale=dim ** -0.5, seed=101).half()
+    b1 = _rand(hidden, seed=102).float()
+    w2 = _rand(hidden, hidden, scale=hidden ** -0.5, seed=103).half()
+    b2 = _rand(hidden, seed=104).float()
+    out = torch.zeros(B, hidden, device=DEV)
+    ws = torch.zeros(B * (dim + hidden), device=DEV)
+    ops.time_embed(t, w1, b1, w2, b2, out, ws, dim=dim, hidden=hidden, accumulate=False)
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=DEV) / half)
+    args = t[:, None] * freqs[None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    ref = F.linear(F.silu(F.linear(emb, w1.float(), b1)), w2.float(), b2)
+    _close(out, ref, "time_embed", rel=1e-3, abs_=1e-3)
+    ops.time_embed(t, w1, b1, w2, b2, out, ws, dim=dim, hidden=hidden, accumulate=True)
+    _close(out, 2 * ref, "time_embed accumulate", rel=1e-3, abs_=2e-3)
+
+    J = 2240
+    w = _rand(J, hidden, scale=hidden ** -0.5, seed=105).half()
+    b = _rand(J, seed=106).float()
+    y = torch.zeros(B, J, dtype=torch.float16, device=DEV)
+    ops.small_linear(ref.contiguous(), w, b, y, silu_in=True)
+    _close(y, F.linear(F.silu(ref), w.float(), b), "small_linear")
+
+
+def _ddim_ref(e_c, e_uc, x, noise, coef):
+    s, phi, sqrt_ac, sqrt_1mac, rescale, sqrt_aprev, dir_coef, sigma = coef
+    v = e_uc + s * (e_c - e_uc)                                   # fp16 tensor arithmetic, as ddim.py:226
+    if phi > 0:
+        dims = list(range(1, v.ndim))
+        std_text = e_c.std(dim=dims, keepdim=True)
+        std_cfg = v.std(dim=dims, keepdim=True)
+        v = phi * (v * (std_text / std_cfg)) + (1 - phi) * v
+    eps = sqrt_ac * v + sqrt_1mac * x
+    x0 = (sqrt_ac * x - sqrt_1mac * v) * rescale
+    return sqrt_aprev * x0 + dir_coef * eps + sigma * noise, x0
+
+
+@pytest.mark.parametrize("phi", [0.7, 0.0])
+def test_ddim_step(ops, phi):
+    B, shape = 2, (4, 16, 40, 64)
+    n = 4 * 16 * 40 * 64
+    e_c = _rand(B, *shape, seed=111).half()
+    e_uc = (e_c.float() + 0.3 * _rand(B, *shape, seed=112)).half()
+    x = _rand(B, *shape, seed=113)
+    noise = _rand(B, *shape, seed=114)
+    coef_l = [7.5, phi, 0.6, 0.8, 0.98, 0.7, 0.3, 0.5]
+    coef = torch.tensor(coef_l, device=DEV)
+    x_prev = torch.zeros_like(x)
+    x0 = torch.zeros_like(x)
+    ws = torch.zeros(4 * B * 64, dtype=torch.float64, device=DEV)
+    ops.ddim_step(e_c, e_uc, x, noise, x_prev, x0, coef, ws, B=B, n=n)
+    ref_prev, ref_x0 = _ddim_ref(e_c, e_uc, x, noise, coef_l)
+    # the CFG mix is fp16 arithmetic in both; allow one fp16 ulp of |v| (~8) propagated through the update
+    _close(x0, ref_x0, "ddim pred_x0", rel=2e-3, abs_=2e-3)
+    _close(x_prev, ref_prev, "ddim x_prev", rel=2e-3, abs_=2e-3)

@@ -1,0 +1,487 @@
+// tooncrafter_b200 — attention kernels.
+//
+//  tc_attention           fused softmax(QK^T)V, head dim 64, tcgen05 MMAs (S = QK^T and O = PV) with TMEM
+//                         accumulators, TMA-staged Q/K/V tiles, fp32 online softmax, one query row per thread.
+//                         Two CTAs per SM: one CTA's softmax overlaps the other's MMAs.
+//  tc_temporal_attention  16-frame temporal self-attention, one (pixel, head) per half-warp (memory-bound).
+//  tc_softmax_rows        row softmax for the unfused d=512 VAE mid-block attention.
+//
+// Reference sites: lvdm/modules/attention.py:81-209,365-412; lvdm/models/autoencoder_dualref.py:172-200,270-341.
+#include "tc_common.cuh"
+#include "tc_host.h"
+
+namespace {
+
+// ===================================================================================== fused attention (d = 64)
+constexpr int kQTile = 128;
+constexpr int kKVTile = 128;
+constexpr int kTileBytes = 128 * 64 * 2;  // 16 KiB: [128 rows][64 halfs], 128B-swizzled
+constexpr int kAttnThreads = 128;
+constexpr int kAttnTmemCols = 256;  // S: cols [0,128), O_blk: cols [128,192)
+
+struct alignas(64) AttnKParams {
+    CUtensorMap tmQ;
+    CUtensorMap tmK[2];
+    CUtensorMap tmV[2];
+    int Lq, heads, n_seg;
+    int Lk[2];
+    int kv_div[2];
+    __half* out;
+    long long ldo;
+    float scale_log2;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 2) tc_attn_kernel(const __grid_constant__ AttnKParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + kTileBytes;
+    uint8_t* sV = smem + 2 * kTileBytes;
+    uint8_t* sP = smem + 3 * kTileBytes;  // two [128][64] sub-tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * kTileBytes);
+    uint64_t* bar_q = bars + 0;
+    uint64_t* bar_k = bars + 1;
+    uint64_t* bar_v = bars + 2;
+    uint64_t* bar_s = bars + 3;
+    uint64_t* bar_o = bars + 4;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 5);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int q0 = blockIdx.x * kQTile;
+    const int head = blockIdx.y;
+    const int qb = blockIdx.z;
+    const bool issuer = (tid == 0);
+
+    if (issuer) {
+        tc::tma_prefetch_desc(&p.tmQ);
+        for (int i = 0; i < 5; ++i) tc::mbar_init(&bars[i], 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 0) {
+        tc::tmem_alloc(tmem_ptr_smem, kAttnTmemCols);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_s = tmem_base;
+    const uint32_t tmem_o = tmem_base + 128;
+    const uint32_t lane_off = ((uint32_t)(warp * 32)) << 16;
+
+    const uint32_t sQ_a = tc::smem_u32(sQ), sK_a = tc::smem_u32(sK), sV_a = tc::smem_u32(sV), sP_a = tc::smem_u32(sP);
+
+    uint32_t ph_k = 0, ph_v = 0, ph_s = 0, ph_o = 0;
+    if (issuer) {
+        tc::mbar_arrive_expect_tx(bar_q, kTileBytes);
+        tc::tma_load_3d(sQ, &p.tmQ, bar_q, head * 64, q0, qb);
+    }
+
+    float o_total[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o_total[i] = 0.f;
+
+    for (int seg = 0; seg < p.n_seg; ++seg) {
+        const int Lk = p.Lk[seg];
+        const int kvb = qb / p.kv_div[seg];
+        const int nblk = (Lk + kKVTile - 1) / kKVTile;
+        const CUtensorMap* tmK = &p.tmK[seg];
+        const CUtensorMap* tmV = &p.tmV[seg];
+
+        if (issuer) {
+            tc::mbar_arrive_expect_tx(bar_k, kTileBytes);
+            tc::tma_load_3d(sK, tmK, bar_k, head * 64, 0, kvb);
+            tc::mbar_arrive_expect_tx(bar_v, kTileBytes);
+            tc::tma_load_3d(sV, tmV, bar_v, head * 64, 0, kvb);
+            if (seg == 0) tc::mbar_wait(bar_q, 0);
+            tc::mbar_wait(bar_k, ph_k);
+            ph_k ^= 1u;
+            tc::tc_fence_after();
+            int nk0 = Lk < kKVTile ? ((Lk + 15) & ~15) : kKVTile;
+            const uint32_t idesc_s = tc::umma_idesc_f16(128, (uint32_t)nk0, 0, 0);
+            const uint64_t qd = tc::umma_desc_sw128(sQ_a), kd = tc::umma_desc_sw128(sK_a);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc::umma_f16(tmem_s, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, k != 0);
+            tc::umma_commit(bar_s);
+        }
+
+        float m_run = -INFINITY, l_run = 0.f;
+        float o_acc[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+
+        for (int j = 0; j < nblk; ++j) {
+            const int kv_left = Lk - j * kKVTile;
+            const int nvalid = kv_left < kKVTile ? kv_left : kKVTile;
+            const int nk = (nvalid + 15) & ~15;  // keys covered by the MMAs of this block
+
+            tc::mbar_wait(bar_s, ph_s);
+            ph_s ^= 1u;
+            tc::tc_fence_after();
+            if (issuer && j + 1 < nblk) {  // S_j done -> K buffer is free
+                tc::mbar_arrive_expect_tx(bar_k, kTileBytes);
+                tc::tma_load_3d(sK, tmK, bar_k, head * 64, (j + 1) * kKVTile, kvb);
+            }
+
+            // ---- pass 1: row max
+            float m_blk = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (c * 16 < nk) {
+                    uint32_t r[16];
+                    tc::tmem_ld16(tmem_s + lane_off + (uint32_t)(c * 16), r);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c * 16 + i < nvalid) m_blk = fmaxf(m_blk, __uint_as_float(r[i]));
+                }
+            }
+            const float m_new = fmaxf(m_run, m_blk);
+            const float m_scaled = m_new * p.scale_log2;
+            const float alpha = fast_exp2(m_run * p.scale_log2 - m_scaled);  // 0 when m_run = -inf
+            // ---- pass 2: p = exp2(s*scale - m*scale), row sum, P tile (fp16, K-major 128B swizzle) to smem
+            float l_blk = 0.f;
+            const int row = tid;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (c * 16 < nk) {
+                    uint32_t r[16];
+                    tc::tmem_ld16(tmem_s + lane_off + (uint32_t)(c * 16), r);
+                    tc::tmem_ld_wait();
+                    float pv[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float e = fast_exp2(__uint_as_float(r[i]) * p.scale_log2 - m_scaled);
+                        pv[i] = (c * 16 + i < nvalid) ? e : 0.f;
+                        l_blk += pv[i];
+                    }
+                    uint4 u0, u1;
+                    __half2 h[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(pv[2 * i], pv[2 * i + 1]);
+                    u0.x = *reinterpret_cast<uint32_t*>(&h[0]);
+                    u0.y = *reinterpret_cast<uint32_t*>(&h[1]);
+                    u0.z = *reinterpret_cast<uint32_t*>(&h[2]);
+                    u0.w = *reinterpret_cast<uint32_t*>(&h[3]);
+                    u1.x = *reinterpret_cast<uint32_t*>(&h[4]);
+                    u1.y = *reinterpret_cast<uint32_t*>(&h[5]);
+                    u1.z = *reinterpret_cast<uint32_t*>(&h[6]);
+                    u1.w = *reinterpret_cast<uint32_t*>(&h[7]);
+                    uint8_t* sub = sP + (c >> 2) * kTileBytes + row * 128;
+                    const int ch0 = (c & 3) * 2;
+                    *reinterpret_cast<uint4*>(sub + (((ch0) ^ (row & 7)) << 4)) = u0;
+                    *reinterpret_cast<uint4*>(sub + (((ch0 + 1) ^ (row & 7)) << 4)) = u1;
+                }
+            }
+            l_run = l_run * alpha + l_blk;
+            m_run = m_new;
+
+            tc::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            tc::tc_fence_before();
+            __syncthreads();
+            if (issuer) {
+                tc::tc_fence_after();
+                tc::mbar_wait(bar_v, ph_v);
+                ph_v ^= 1u;
+                tc::tc_fence_after();
+                const uint32_t idesc_o = tc::umma_idesc_f16(128, 64, 0, 1);  // B (= V tile) is MN-major
+                const uint64_t vd = tc::umma_desc_sw128(sV_a);
+                for (int t = 0; t < nk / 16; ++t) {
+                    const uint64_t pd = tc::umma_desc_sw128(sP_a + (uint32_t)(t >> 2) * kTileBytes) + (uint64_t)((t & 3) * 2);
+                    tc::umma_f16(tmem_o, pd, vd + (uint64_t)(t * 128), idesc_o, t != 0);
+                }
+                tc::umma_commit(bar_o);
+                if (j + 1 < nblk) {
+                    tc::mbar_wait(bar_k, ph_k);
+                    ph_k ^= 1u;
+                    tc::tc_fence_after();
+                    const int left = Lk - (j + 1) * kKVTile;
+                    const int nk1 = left < kKVTile ? ((left + 15) & ~15) : kKVTile;
+                    const uint32_t idesc_s = tc::umma_idesc_f16(128, (uint32_t)nk1, 0, 0);
+                    const uint64_t qd = tc::umma_desc_sw128(sQ_a), kd = tc::umma_desc_sw128(sK_a);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::umma_f16(tmem_s, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, k != 0);
+                    tc::umma_commit(bar_s);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 64; ++i) o_acc[i] *= alpha;
+
+            tc::mbar_wait(bar_o, ph_o);
+            ph_o ^= 1u;
+            tc::tc_fence_after();
+            if (issuer && j + 1 < nblk) {  // PV_j done -> V buffer is free
+                tc::mbar_arrive_expect_tx(bar_v, kTileBytes);
+                tc::tma_load_3d(sV, tmV, bar_v, head * 64, (j + 1) * kKVTile, kvb);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[16];
+                tc::tmem_ld16(tmem_o + lane_off + (uint32_t)(c * 16), r);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] += __uint_as_float(r[i]);
+            }
+        }
+        const float inv_l = 1.0f / l_run;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) o_total[i] += o_acc[i] * inv_l;
+    }
+
+    const int qrow = q0 + tid;
+    if (qrow < p.Lq) {
+        __half* dst = p.out + ((long long)qb * p.Lq + qrow) * p.ldo + head * 64;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            __half2 h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(o_total[c * 8 + 2 * i], o_total[c * 8 + 2 * i + 1]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h[0]);
+            u.y = *reinterpret_cast<uint32_t*>(&h[1]);
+            u.z = *reinterpret_cast<uint32_t*>(&h[2]);
+            u.w = *reinterpret_cast<uint32_t*>(&h[3]);
+            reinterpret_cast<uint4*>(dst)[c] = u;
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, kAttnTmemCols);
+    }
+}
+
+// ===================================================================================== temporal attention
+// x[b][t][p][heads*64]; one (b, p, head) item per group of kGroup lanes (lane i of the group = query frame i).
+template <int kGroup>
+__global__ void temporal_attn_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
+                                     const __half* __restrict__ v, long long ld, __half* __restrict__ out,
+                                     long long ldo, int B, int T, int P, int heads, float scale_log2) {
+    constexpr int kItemsPerWarp = 32 / kGroup;
+    constexpr int kWarps = 4;
+    __shared__ __align__(16) __half sK[kWarps * kItemsPerWarp][kGroup][64];
+    __shared__ __align__(16) __half sV[kWarps * kItemsPerWarp][kGroup][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane / kGroup, t = lane % kGroup;
+    const long long total = (long long)B * P * heads;
+    const long long item = ((long long)blockIdx.x * kWarps + warp) * kItemsPerWarp + sub;
+    const bool item_ok = item < total;
+    const int slot = warp * kItemsPerWarp + sub;
+
+    long long b = 0, pix = 0;
+    int h = 0;
+    if (item_ok) {
+        h = (int)(item % heads);
+        const long long r = item / heads;
+        pix = r % P;
+        b = r / P;
+    }
+    const bool row_ok = item_ok && t < T;
+    const long long tok = ((b * T + t) * P + pix);
+    float qf[64];
+    if (row_ok) {
+        const uint4* qp = reinterpret_cast<const uint4*>(q + tok * ld + h * 64);
+        const uint4* kp = reinterpret_cast<const uint4*>(k + tok * ld + h * 64);
+        const uint4* vp = reinterpret_cast<const uint4*>(v + tok * ld + h * 64);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 u = qp[c];
+            const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(hh[i]);
+                qf[c * 8 + 2 * i] = f.x;
+                qf[c * 8 + 2 * i + 1] = f.y;
+            }
+            reinterpret_cast<uint4*>(&sK[slot][t][0])[c] = kp[c];
+            reinterpret_cast<uint4*>(&sV[slot][t][0])[c] = vp[c];
+        }
+    }
+    __syncwarp();
+    if (!row_ok) return;
+
+    float s[kGroup];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kGroup; ++j) {
+        if (j < T) {
+            float acc = 0.f;
+            const __half2* kr = reinterpret_cast<const __half2*>(&sK[slot][j][0]);
+#pragma unroll
+            for (int d = 0; d < 32; ++d) {
+                const float2 f = __half22float2(kr[d]);
+                acc += qf[2 * d] * f.x + qf[2 * d + 1] * f.y;
+            }
+            s[j] = acc * scale_log2;
+            m = fmaxf(m, s[j]);
+        }
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < kGroup; ++j) {
+        if (j < T) {
+            s[j] = exp2f(s[j] - m);
+            l += s[j];
+        }
+    }
+    const float inv = 1.0f / l;
+    float o[64];
+#pragma unroll
+    for (int d = 0; d < 64; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kGroup; ++j) {
+        if (j < T) {
+            const float pj = s[j] * inv;
+            const __half2* vr = reinterpret_cast<const __half2*>(&sV[slot][j][0]);
+#pragma unroll
+            for (int d = 0; d < 32; ++d) {
+                const float2 f = __half22float2(vr[d]);
+                o[2 * d] += pj * f.x;
+                o[2 * d + 1] += pj * f.y;
+            }
+        }
+    }
+    __half* dst = out + tok * ldo + h * 64;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        __half2 hh[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hh[i] = __floats2half2_rn(o[c * 8 + 2 * i], o[c * 8 + 2 * i + 1]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&hh[0]);
+        u.y = *reinterpret_cast<uint32_t*>(&hh[1]);
+        u.z = *reinterpret_cast<uint32_t*>(&hh[2]);
+        u.w = *reinterpret_cast<uint32_t*>(&hh[3]);
+        reinterpret_cast<uint4*>(dst)[c] = u;
+    }
+}
+
+// ===================================================================================== row softmax (in place)
+__global__ void softmax_rows_kernel(__half* __restrict__ s, long long lds, int rows, int cols, float scale_log2) {
+    const int row = blockIdx.x;
+    if (row >= rows) return;
+    __half* r = s + (long long)row * lds;
+    __shared__ float red[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float m = -INFINITY;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, __half2float(r[c]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < nw; ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float l = 0.f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) l += exp2f((__half2float(r[c]) - m) * scale_log2);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    if (lane == 0) red[warp] = l;
+    __syncthreads();
+    l = 0.f;
+    for (int w = 0; w < nw; ++w) l += red[w];
+    const float inv = 1.0f / l;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x)
+        r[c] = __float2half_rn(exp2f((__half2float(r[c]) - m) * scale_log2) * inv);
+}
+
+}  // namespace
+
+using namespace tc_host;
+
+extern "C" int tc_attention(const TcAttention* d, void* stream_v) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    TC_CHECK_ARG(d && d->q && d->out, "tc_attention: null pointer");
+    TC_CHECK_ARG(d->n_seg == 1 || d->n_seg == 2, "tc_attention: n_seg must be 1 or 2");
+    TC_CHECK_ARG(d->q_batches > 0 && d->Lq > 0 && d->heads > 0, "tc_attention: empty problem");
+    TC_CHECK_ARG(d->ldq % 8 == 0 && d->ldo % 8 == 0, "tc_attention: strides must be multiples of 8");
+    AttnKParams p;
+    memset(&p, 0, sizeof(p));
+    const uint32_t box[3] = {64, 128, 1};
+    {
+        uint64_t dims[3] = {(uint64_t)d->heads * 64, (uint64_t)d->Lq, (uint64_t)d->q_batches};
+        uint64_t str[2] = {(uint64_t)d->ldq * 2, (uint64_t)d->Lq * (uint64_t)d->ldq * 2};
+        const CUtensorMap* m = get_tensor_map(d->q, 3, dims, str, box);
+        if (!m) return TC_ERR_CUDA;
+        p.tmQ = *m;
+    }
+    for (int s = 0; s < d->n_seg; ++s) {
+        TC_CHECK_ARG(d->k[s] && d->v[s] && d->Lk[s] > 0 && d->kv_div[s] > 0, "tc_attention: bad kv segment");
+        TC_CHECK_ARG(d->ldk[s] % 8 == 0 && d->ldv[s] % 8 == 0, "tc_attention: kv strides must be multiples of 8");
+        const int kvb = (d->q_batches + d->kv_div[s] - 1) / d->kv_div[s];
+        uint64_t dims[3] = {(uint64_t)d->heads * 64, (uint64_t)d->Lk[s], (uint64_t)kvb};
+        uint64_t strk[2] = {(uint64_t)d->ldk[s] * 2, (uint64_t)d->Lk[s] * (uint64_t)d->ldk[s] * 2};
+        uint64_t strv[2] = {(uint64_t)d->ldv[s] * 2, (uint64_t)d->Lk[s] * (uint64_t)d->ldv[s] * 2};
+        const CUtensorMap* mk = get_tensor_map(d->k[s], 3, dims, strk, box);
+        const CUtensorMap* mv = get_tensor_map(d->v[s], 3, dims, strv, box);
+        if (!mk || !mv) return TC_ERR_CUDA;
+        p.tmK[s] = *mk;
+        p.tmV[s] = *mv;
+        p.Lk[s] = d->Lk[s];
+        p.kv_div[s] = d->kv_div[s];
+    }
+    p.Lq = d->Lq;
+    p.heads = d->heads;
+    p.n_seg = d->n_seg;
+    p.out = reinterpret_cast<__half*>(d->out);
+    p.ldo = d->ldo;
+    p.scale_log2 = d->scale * 1.4426950408889634f;
+    const size_t smem_bytes = 5 * kTileBytes + 1024 + 128;
+    static bool attr_set = false;
+    if (!attr_set) {
+        int rc = check_cuda(
+            cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
+            "cudaFuncSetAttribute(tc_attn_kernel)");
+        if (rc) return rc;
+        attr_set = true;
+    }
+    dim3 grid((d->Lq + kQTile - 1) / kQTile, d->heads, d->q_batches);
+    tc_attn_kernel<<<grid, kAttnThreads, smem_bytes, stream>>>(p);
+    count_launch();
+    TC_CHECK_LAUNCH("tc_attn_kernel");
+    return TC_OK;
+}
+
+extern "C" int tc_temporal_attention(const void* q, const void* k, const void* v, long long ld, void* out,
+                                     long long ldo, int B, int T, int P, int heads, float scale, void* stream_v) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    TC_CHECK_ARG(q && k && v && out, "tc_temporal_attention: null pointer");
+    TC_CHECK_ARG(B > 0 && T > 0 && T <= 32 && P > 0 && heads > 0, "tc_temporal_attention: need 0 < T <= 32");
+    TC_CHECK_ARG(ld % 8 == 0 && ldo % 8 == 0, "tc_temporal_attention: strides must be multiples of 8");
+    const long long items = (long long)B * P * heads;
+    const float sl2 = scale * 1.4426950408889634f;
+    const __half* qp = reinterpret_cast<const __half*>(q);
+    const __half* kp = reinterpret_cast<const __half*>(k);
+    const __half* vp = reinterpret_cast<const __half*>(v);
+    __half* op = reinterpret_cast<__half*>(out);
+    if (T <= 16) {
+        const long long blocks = (items + 7) / 8;
+        temporal_attn_kernel<16><<<(unsigned)blocks, 128, 0, stream>>>(qp, kp, vp, ld, op, ldo, B, T, P, heads, sl2);
+    } else {
+        const long long blocks = (items + 3) / 4;
+        temporal_attn_kernel<32><<<(unsigned)blocks, 128, 0, stream>>>(qp, kp, vp, ld, op, ldo, B, T, P, heads, sl2);
+    }
+    count_launch();
+    TC_CHECK_LAUNCH("temporal_attn_kernel");
+    return TC_OK;
+}
+
+extern "C" int tc_softmax_rows(void* s, long long lds, int rows, int cols, float scale, void* stream_v) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    TC_CHECK_ARG(s && rows > 0 && cols > 0, "tc_softmax_rows: bad arguments");
+    softmax_rows_kernel<<<rows, 256, 0, stream>>>(reinterpret_cast<__half*>(s), lds, rows, cols,
+                                                  scale * 1.4426950408889634f);
+    count_launch();
+    TC_CHECK_LAUNCH("softmax_rows_kernel");
+    return TC_OK;
+}

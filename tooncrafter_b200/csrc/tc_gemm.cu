@@ -1,0 +1,435 @@
+// tooncrafter_b200 — implicit-GEMM convolution / linear layer on tcgen05 (sm_100a).
+//
+// One persistent, warp-specialised kernel serves every dense contraction of the UNet and the VAE decoder
+// (reference call sites listed in include/tooncrafter_b200.h):
+//
+//   warp 0      TMA producer   : per k-block one 4-D box of the channels-last activation (im2col by
+//                                coordinate offset; out-of-bounds rows/cols are zero-filled by TMA == padding)
+//                                and one 2-D box of the [Cout][taps*C] weight matrix, 128B-swizzled
+//   warp 1      MMA issuer     : tcgen05.mma cta_group::1 kind::f16, M=128 x N=block_n x K=16, fp32 accum in TMEM,
+//                                two accumulator buffers so the epilogue of tile i overlaps the mainloop of i+1
+//   warps 2..5  epilogue       : tcgen05.ld (one output row per thread) -> +bias, +per-sample embedding,
+//                                *scale, +residual, optional GEGLU -> fp16 -> 16-byte global stores
+//
+// Roofline: tensor-bound (fp16 dense); algorithmic flops = 2 * M * n_cols * taps * C.
+#include "tc_common.cuh"
+#include "tc_host.h"
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                          // 64 halfs = one 128-byte swizzle row
+constexpr int kAStageBytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;  // TMEM column offset of the second accumulator
+
+struct alignas(64) GemmKParams {
+    CUtensorMap tmA;
+    CUtensorMap tmB;
+    int taps;
+    int tap_dx[TC_MAX_TAPS], tap_dy[TC_MAX_TAPS], tap_dn[TC_MAX_TAPS];
+    int kc_per_tap;
+    int TW, TH, TN;
+    int oW, oH, oN;
+    int tiles_x, tiles_y, tiles_n;  // spatial tiling of the M dimension
+    int tiles_m, tiles_nn;          // tiles along M and along N
+    int BN;
+    int n_cols;
+    int stages;
+    uint32_t a_bytes;  // bytes delivered per A box
+    __half* out;
+    long long ldc;
+    const float* bias;
+    const __half* bias2;
+    long long bias2_ld;
+    int bias2_rows_per;
+    const __half* res;
+    long long ldr;
+    float acc_scale;
+    int flags;
+};
+
+__device__ __forceinline__ void store_row16(__half* dst, const float (&v)[16], int ncols_valid) {
+    if (ncols_valid >= 16) {
+        uint4 u0, u1;
+        __half2 h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        u0.x = *reinterpret_cast<uint32_t*>(&h[0]);
+        u0.y = *reinterpret_cast<uint32_t*>(&h[1]);
+        u0.z = *reinterpret_cast<uint32_t*>(&h[2]);
+        u0.w = *reinterpret_cast<uint32_t*>(&h[3]);
+        u1.x = *reinterpret_cast<uint32_t*>(&h[4]);
+        u1.y = *reinterpret_cast<uint32_t*>(&h[5]);
+        u1.z = *reinterpret_cast<uint32_t*>(&h[6]);
+        u1.w = *reinterpret_cast<uint32_t*>(&h[7]);
+        reinterpret_cast<uint4*>(dst)[0] = u0;
+        reinterpret_cast<uint4*>(dst)[1] = u1;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < ncols_valid) dst[i] = __float2half_rn(v[i]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ GemmKParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int S = p.stages;
+    const int BN = p.BN;
+    const uint32_t b_stage_bytes = (uint32_t)BN * 128u;
+
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)S * kAStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + (size_t)S * b_stage_bytes);
+    uint64_t* empty_bar = full_bar + S;
+    uint64_t* tfull_bar = empty_bar + S;   // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;  // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&p.tmA);
+        tc::tma_prefetch_desc(&p.tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < S; ++s) {
+            tc::mbar_init(&full_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(&tfull_bar[a], 1);
+            tc::mbar_init(&tempty_bar[a], 4);
+        }
+        tc::fence_mbar_init();
+    }
+    if (warp == 2) {
+        tc::tmem_alloc(tmem_ptr_smem, kTmemCols);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int total_tiles = p.tiles_m * p.tiles_nn;
+    const int kblocks = p.taps * p.kc_per_tap;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile / p.tiles_m;
+                const int mt = tile - nt * p.tiles_m;
+                const int tx = mt % p.tiles_x;
+                const int ty = (mt / p.tiles_x) % p.tiles_y;
+                const int tn = mt / (p.tiles_x * p.tiles_y);
+                const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap], an = n0 + p.tap_dn[tap];
+                    for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+                        tc::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        tc::mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + b_stage_bytes);
+                        tc::tma_load_4d(sA + (size_t)stage * kAStageBytes, &p.tmA, &full_bar[stage], kc * kBlockK, ax,
+                                        ay, an);
+                        tc::tma_load_2d(sB + (size_t)stage * b_stage_bytes, &p.tmB, &full_bar[stage],
+                                        (tap * p.kc_per_tap + kc) * kBlockK, nt * BN);
+                        if (++stage == S) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = tc::umma_idesc_f16(kBlockM, (uint32_t)BN, 0, 0);
+            const uint32_t sA_addr = tc::smem_u32(sA), sB_addr = tc::smem_u32(sB);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    tc::mbar_wait(&full_bar[stage], phase);
+                    tc::tc_fence_after();
+                    const uint64_t a_desc = tc::umma_desc_sw128(sA_addr + (uint32_t)stage * kAStageBytes);
+                    const uint64_t b_desc = tc::umma_desc_sw128(sB_addr + (uint32_t)stage * b_stage_bytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // advance 16 halfs = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
+                        tc::umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                     (kb | k) != 0 ? 1u : 0u);
+                    }
+                    tc::umma_commit(&empty_bar[stage]);
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                tc::umma_commit(&tfull_bar[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;
+        const int rx = row % p.TW;
+        const int ry = (row / p.TW) % p.TH;
+        const int rn = row / (p.TW * p.TH);
+        const bool geglu = (p.flags & TC_EPI_GEGLU) != 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile / p.tiles_m;
+            const int mt = tile - nt * p.tiles_m;
+            const int tx = mt % p.tiles_x;
+            const int ty = (mt / p.tiles_x) % p.tiles_y;
+            const int tn = mt / (p.tiles_x * p.tiles_y);
+            const int x = tx * p.TW + rx, y = ty * p.TH + ry, n = tn * p.TN + rn;
+            const bool row_ok = (rn < p.TN) && (x < p.oW) && (y < p.oH) && (n < p.oN);
+            const long long m = ((long long)n * p.oH + y) * p.oW + x;
+
+            tc::mbar_wait(&tfull_bar[acc], acc_phase);
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(q * 32) << 16);
+
+            if (!geglu) {
+                __half* orow = p.out + m * p.ldc;
+                const __half* rrow = p.res ? p.res + m * p.ldr : nullptr;
+                const __half* b2row =
+                    p.bias2 ? p.bias2 + (row_ok ? (m / p.bias2_rows_per) : 0) * p.bias2_ld : nullptr;
+                for (int c = 0; c < BN; c += 16) {
+                    uint32_t r[16];
+                    tc::tmem_ld16(taddr + (uint32_t)c, r);
+                    tc::tmem_ld_wait();
+                    const int col0 = nt * BN + c;
+                    const int nvalid = p.n_cols - col0;
+                    if (row_ok && nvalid > 0) {
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                        if (p.bias) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (i < nvalid) v[i] += p.bias[col0 + i];
+                        }
+                        if (b2row) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (i < nvalid) v[i] += __half2float(b2row[col0 + i]);
+                        }
+                        if (p.acc_scale != 1.0f) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] *= p.acc_scale;
+                        }
+                        if (rrow) {
+                            if (nvalid >= 16) {
+                                const uint4 u0 = reinterpret_cast<const uint4*>(rrow + col0)[0];
+                                const uint4 u1 = reinterpret_cast<const uint4*>(rrow + col0)[1];
+                                const __half2* h0 = reinterpret_cast<const __half2*>(&u0);
+                                const __half2* h1 = reinterpret_cast<const __half2*>(&u1);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float2 f0 = __half22float2(h0[i]);
+                                    const float2 f1 = __half22float2(h1[i]);
+                                    v[2 * i] += f0.x;
+                                    v[2 * i + 1] += f0.y;
+                                    v[8 + 2 * i] += f1.x;
+                                    v[8 + 2 * i + 1] += f1.y;
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (i < nvalid) v[i] += __half2float(rrow[col0 + i]);
+                            }
+                        }
+                        store_row16(orow + col0, v, nvalid);
+                    }
+                }
+            } else {
+                // weight rows of this N tile are [a-half (BN/2) | gate-half (BN/2)]; output tile is BN/2 wide
+                const int half_bn = BN >> 1;
+                __half* orow = p.out + m * p.ldc + (long long)nt * half_bn;
+                for (int c = 0; c < half_bn; c += 16) {
+                    uint32_t ra[16], rg[16];
+                    tc::tmem_ld16(taddr + (uint32_t)c, ra);
+                    tc::tmem_ld16(taddr + (uint32_t)(half_bn + c), rg);
+                    tc::tmem_ld_wait();
+                    if (row_ok) {
+                        float v[16];
+                        const int ca = nt * BN + c, cg = nt * BN + half_bn + c;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float a = __uint_as_float(ra[i]);
+                            float g = __uint_as_float(rg[i]);
+                            if (p.bias) {
+                                a += p.bias[ca + i];
+                                g += p.bias[cg + i];
+                            }
+                            v[i] = a * tc::gelu_erf_f(g);
+                        }
+                        store_row16(orow + c, v, 16);
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+int pick_block_n(int n_cols) {
+    const int n16 = (n_cols + 15) / 16 * 16;
+    if (n16 <= 256) return n16;
+    // largest multiple of 16 <= 256 that divides n16, but not smaller than 128
+    for (int bn = 256; bn >= 128; bn -= 16)
+        if (n16 % bn == 0) return bn;
+    return 256;
+}
+
+}  // namespace
+
+extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
+    using namespace tc_host;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    TC_CHECK_ARG(d != nullptr, "tc_conv_gemm: null descriptor");
+    TC_CHECK_ARG(d->a && d->b && d->out, "tc_conv_gemm: null operand pointer");
+    TC_CHECK_ARG(d->a_C > 0 && d->a_C % kBlockK == 0, "tc_conv_gemm: C must be a positive multiple of 64");
+    TC_CHECK_ARG(d->taps >= 1 && d->taps <= TC_MAX_TAPS, "tc_conv_gemm: taps out of range");
+    TC_CHECK_ARG(d->oN > 0 && d->oH > 0 && d->oW > 0 && d->n_cols > 0, "tc_conv_gemm: empty problem");
+    TC_CHECK_ARG((reinterpret_cast<uintptr_t>(d->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->b) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
+                 "tc_conv_gemm: operands must be 16-byte aligned");
+    TC_CHECK_ARG(d->a_sW % 8 == 0 && d->a_sH % 8 == 0 && d->a_sN % 8 == 0 && d->ldb % 8 == 0 && d->ldc % 8 == 0,
+                 "tc_conv_gemm: strides must be multiples of 8 elements");
+    TC_CHECK_ARG(!d->res || (d->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(d->res) & 15) == 0),
+                 "tc_conv_gemm: residual must be 16-byte aligned");
+    const bool geglu = (d->flags & TC_EPI_GEGLU) != 0;
+    int BN = d->block_n > 0 ? d->block_n : pick_block_n(d->n_cols);
+    TC_CHECK_ARG(BN % 16 == 0 && BN >= 16 && BN <= 256, "tc_conv_gemm: block_n must be a multiple of 16 in [16,256]");
+    if (geglu) {
+        TC_CHECK_ARG(BN % 32 == 0 && d->n_cols % BN == 0, "tc_conv_gemm: GEGLU needs n_cols % block_n == 0");
+        TC_CHECK_ARG(!d->res && !d->bias2, "tc_conv_gemm: GEGLU epilogue takes bias only");
+    }
+
+    GemmKParams p;
+    memset(&p, 0, sizeof(p));
+    // --- M tiling: (TW, TH, TN) box of output pixels, TW*TH*TN <= 128, minimising the tile count
+    int bestTW = 1, bestTH = 1, bestTN = 1;
+    long long best_tiles = -1;
+    const int maxW = d->oW < kBlockM ? d->oW : kBlockM;
+    for (int TW = 1; TW <= maxW; ++TW) {
+        int maxH = kBlockM / TW;
+        if (maxH > d->oH) maxH = d->oH;
+        for (int TH = 1; TH <= maxH; ++TH) {
+            int TN = kBlockM / (TW * TH);
+            if (TN > d->oN) TN = d->oN;
+            if (TN < 1) continue;
+            if (TN > 1 && (TH != d->oH || TW != d->oW)) TN = 1;  // multi-frame boxes only over whole frames
+            const long long tiles = (long long)((d->oW + TW - 1) / TW) * ((d->oH + TH - 1) / TH) *
+                                    ((d->oN + TN - 1) / TN);
+            if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && TW > bestTW)) {
+                best_tiles = tiles;
+                bestTW = TW;
+                bestTH = TH;
+                bestTN = TN;
+            }
+        }
+    }
+    p.TW = bestTW;
+    p.TH = bestTH;
+    p.TN = bestTN;
+    p.oW = d->oW;
+    p.oH = d->oH;
+    p.oN = d->oN;
+    p.tiles_x = (d->oW + p.TW - 1) / p.TW;
+    p.tiles_y = (d->oH + p.TH - 1) / p.TH;
+    p.tiles_n = (d->oN + p.TN - 1) / p.TN;
+    p.tiles_m = p.tiles_x * p.tiles_y * p.tiles_n;
+    p.BN = BN;
+    p.tiles_nn = (d->n_cols + BN - 1) / BN;
+    p.n_cols = d->n_cols;
+    p.taps = d->taps;
+    for (int t = 0; t < d->taps; ++t) {
+        p.tap_dx[t] = d->tap_dx[t];
+        p.tap_dy[t] = d->tap_dy[t];
+        p.tap_dn[t] = d->tap_dn[t];
+    }
+    p.kc_per_tap = d->a_C / kBlockK;
+    p.a_bytes = (uint32_t)(p.TW * p.TH * p.TN) * 128u;
+    p.out = reinterpret_cast<__half*>(d->out);
+    p.ldc = d->ldc;
+    p.bias = d->bias;
+    p.bias2 = reinterpret_cast<const __half*>(d->bias2);
+    p.bias2_ld = d->bias2_ld;
+    p.bias2_rows_per = d->bias2_rows_per > 0 ? d->bias2_rows_per : 1;
+    p.res = reinterpret_cast<const __half*>(d->res);
+    p.ldr = d->ldr;
+    p.acc_scale = d->acc_scale;
+    p.flags = d->flags;
+
+    // --- tensor maps
+    {
+        uint64_t dims[4] = {(uint64_t)d->a_C, (uint64_t)d->a_W, (uint64_t)d->a_H, (uint64_t)d->a_N};
+        uint64_t strides[3] = {(uint64_t)d->a_sW * 2, (uint64_t)d->a_sH * 2, (uint64_t)d->a_sN * 2};
+        uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+        const CUtensorMap* m = get_tensor_map(d->a, 4, dims, strides, box);
+        if (!m) return TC_ERR_CUDA;
+        p.tmA = *m;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)d->taps * (uint64_t)d->a_C, (uint64_t)d->b_rows};
+        uint64_t strides[1] = {(uint64_t)d->ldb * 2};
+        uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)BN};
+        const CUtensorMap* m = get_tensor_map(d->b, 2, dims, strides, box);
+        if (!m) return TC_ERR_CUDA;
+        p.tmB = *m;
+    }
+
+    const int stage_bytes = kAStageBytes + BN * 128;
+    const int smem_budget = 227 * 1024 - 1024 - 512;
+    int stages = smem_budget / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) return fail(TC_ERR_INVALID, "tc_conv_gemm: not enough shared memory for 2 stages");
+    p.stages = stages;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        int rc = check_cuda(
+            cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+            "cudaFuncSetAttribute(tc_gemm_kernel)");
+        if (rc) return rc;
+        attr_set = true;
+    }
+    const long long total_tiles = (long long)p.tiles_m * p.tiles_nn;
+    int grid = sm_count();
+    if (total_tiles < grid) grid = (int)total_tiles;
+    tc_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+    count_launch();
+    TC_CHECK_LAUNCH("tc_gemm_kernel launch");
+    return TC_OK;
+}

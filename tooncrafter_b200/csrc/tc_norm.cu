@@ -1,0 +1,267 @@
+// tooncrafter_b200 — GroupNorm(+SiLU) and LayerNorm, channels-last fp16, fp32 statistics (HBM-bound).
+//
+// GroupNorm reference sites: lvdm/basics.py:76-87 (GroupNormSpecific, eps 1e-5, 4-D per frame and 5-D per clip),
+// lvdm/modules/attention.py:265,331 (eps 1e-6), openaimodel3d.py:256-265 (5-D), autoencoder_dualref.py:29-32.
+// LayerNorm: lvdm/modules/attention.py:225-227.
+//
+// Algorithmic bytes: GroupNorm = 2 reads + 1 write of the activation (statistics pass + apply pass; the second
+// read hits L2 for UNet-sized tensors); LayerNorm = 1 read + 1 write.
+#include "tc_common.cuh"
+#include "tc_host.h"
+
+namespace {
+
+constexpr int kGnMaxPartials = TC_GN_MAX_PARTIALS;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __half22float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 u;
+    __half2 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    u.x = *reinterpret_cast<uint32_t*>(&h[0]);
+    u.y = *reinterpret_cast<uint32_t*>(&h[1]);
+    u.z = *reinterpret_cast<uint32_t*>(&h[2]);
+    u.w = *reinterpret_cast<uint32_t*>(&h[3]);
+    return u;
+}
+
+// ---- pass 1: per-block partial (sum, sumsq) per group -------------------------------------------------
+// grid = (nblk, n_stat); block = V * k threads (V = C/8), thread t owns channel vector t % V.
+__global__ void gn_stats_kernel(const __half* __restrict__ x, long long ldx, long long pixels_per_stat, int C, int G,
+                                float* __restrict__ partials) {
+    extern __shared__ float sm[];  // [2*C]
+    const int V = C >> 3;
+    const int v = threadIdx.x % V;
+    const int prow = threadIdx.x / V;
+    const int rows_per_iter = blockDim.x / V;
+    const int s = blockIdx.y;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+
+    float sum[8], sq[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
+    const __half* base = x + (long long)s * pixels_per_stat * ldx + (long long)v * 8;
+    for (long long pix = (long long)blockIdx.x * rows_per_iter + prow; pix < pixels_per_stat;
+         pix += (long long)gridDim.x * rows_per_iter) {
+        const uint4 u = *reinterpret_cast<const uint4*>(base + pix * ldx);
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            sum[i] += f[i];
+            sq[i] += f[i] * f[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        atomicAdd(&sm[v * 8 + i], sum[i]);
+        atomicAdd(&sm[C + v * 8 + i], sq[i]);
+    }
+    __syncthreads();
+    const int cpg = C / G;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int c = 0; c < cpg; ++c) {
+            a += sm[g * cpg + c];
+            b += sm[C + g * cpg + c];
+        }
+        float* dst = partials + (((long long)s * gridDim.x + blockIdx.x) * G + g) * 2;
+        dst[0] = a;
+        dst[1] = b;
+    }
+}
+
+// ---- pass 2: finalize statistics for this block's stat group, then normalise (+SiLU) -------------------
+// grid = (blocks_per_stat, n_stat)
+__global__ void gn_apply_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                long long pixels_per_stat, int C, int G, float eps, int silu,
+                                const float* __restrict__ partials, int nblk) {
+    extern __shared__ float sm[];  // mean[G], rstd[G]
+    float* s_mean = sm;
+    float* s_rstd = sm + G;
+    const int s = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int cpg = C / G;
+    for (int g = warp; g < G; g += nwarps) {
+        double a = 0.0, b = 0.0;
+        for (int k = lane; k < nblk; k += 32) {
+            const float* src = partials + (((long long)s * nblk + k) * G + g) * 2;
+            a += (double)src[0];
+            b += (double)src[1];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (lane == 0) {
+            const double cnt = (double)pixels_per_stat * (double)cpg;
+            const double mean = a / cnt;
+            double var = b / cnt - mean * mean;
+            if (var < 0.0) var = 0.0;
+            s_mean[g] = (float)mean;
+            s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+        }
+    }
+    __syncthreads();
+
+    const int V = C >> 3;
+    const int v = threadIdx.x % V;
+    const int prow = threadIdx.x / V;
+    const int rows_per_iter = blockDim.x / V;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = v * 8 + i;
+        const int g = c / cpg;
+        const float a = s_rstd[g] * gamma[c];
+        sc[i] = a;
+        sh[i] = beta[c] - s_mean[g] * a;
+    }
+    const __half* xb = x + (long long)s * pixels_per_stat * ldx + (long long)v * 8;
+    __half* yb = y + (long long)s * pixels_per_stat * ldy + (long long)v * 8;
+    for (long long pix = (long long)blockIdx.x * rows_per_iter + prow; pix < pixels_per_stat;
+         pix += (long long)gridDim.x * rows_per_iter) {
+        const uint4 u = *reinterpret_cast<const uint4*>(xb + pix * ldx);
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float t = f[i] * sc[i] + sh[i];
+            if (silu) t = tc::silu_f(t);
+            f[i] = t;
+        }
+        *reinterpret_cast<uint4*>(yb + pix * ldy) = pack8(f);
+    }
+}
+
+// ---- LayerNorm: one warp per row, row kept in registers ------------------------------------------------
+template <int kMaxVec>
+__global__ void layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int C,
+                                 float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int V = C >> 3;
+    const __half* xr = x + (long long)warp * ldx;
+    float f[kMaxVec][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+        const int v = lane + 32 * i;
+        if (v < V) {
+            const uint4 u = *reinterpret_cast<const uint4*>(xr + v * 8);
+            unpack8(u, f[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sum += f[i][j];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+        const int v = lane + 32 * i;
+        if (v < V) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = f[i][j] - mean;
+                sq += d * d;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)C + eps);
+    __half* yr = y + (long long)warp * ldy;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+        const int v = lane + 32 * i;
+        if (v < V) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = v * 8 + j;
+                o[j] = (f[i][j] - mean) * rstd * gamma[c] + beta[c];
+            }
+            *reinterpret_cast<uint4*>(yr + v * 8) = pack8(o);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int tc_groupnorm(const void* x, long long ldx, void* y, long long ldy, const float* gamma,
+                            const float* beta, int frames, int frames_per_stat, int hw, int C, int G, float eps,
+                            int silu, float* ws, void* stream_v) {
+    using namespace tc_host;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    TC_CHECK_ARG(x && y && gamma && beta && ws, "tc_groupnorm: null pointer");
+    TC_CHECK_ARG(C > 0 && C % 8 == 0 && G > 0 && C % G == 0, "tc_groupnorm: need C % 8 == 0 and C % G == 0");
+    TC_CHECK_ARG(C / 8 <= 512, "tc_groupnorm: C too large (max 4096)");
+    TC_CHECK_ARG(frames > 0 && frames_per_stat > 0 && frames % frames_per_stat == 0 && hw > 0,
+                 "tc_groupnorm: bad frame counts");
+    TC_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0, "tc_groupnorm: strides must be multiples of 8");
+    const int n_stat = frames / frames_per_stat;
+    const long long pps = (long long)frames_per_stat * hw;
+    const int V = C / 8;
+    int k = 512 / V;
+    if (k < 1) k = 1;
+    const int threads = V * k;
+    // each thread should see >= 8 pixels in the statistics pass; cap partial blocks per stat group
+    long long want = (pps + (long long)k * 8 - 1) / ((long long)k * 8);
+    int nblk = (int)(want < 1 ? 1 : want);
+    int cap = (2 * sm_count() + n_stat - 1) / n_stat;
+    if (cap < 1) cap = 1;
+    if (cap > kGnMaxPartials) cap = kGnMaxPartials;
+    if (nblk > cap) nblk = cap;
+    gn_stats_kernel<<<dim3(nblk, n_stat), threads, 2 * C * sizeof(float), stream>>>(
+        reinterpret_cast<const __half*>(x), ldx, pps, C, G, ws);
+    count_launch();
+    TC_CHECK_LAUNCH("gn_stats_kernel");
+    long long want2 = (pps + (long long)k * 4 - 1) / ((long long)k * 4);
+    int nblk2 = (int)(want2 < 1 ? 1 : want2);
+    int cap2 = (8 * sm_count() + n_stat - 1) / n_stat;
+    if (nblk2 > cap2) nblk2 = cap2;
+    gn_apply_kernel<<<dim3(nblk2, n_stat), threads, 2 * G * sizeof(float), stream>>>(
+        reinterpret_cast<const __half*>(x), ldx, reinterpret_cast<__half*>(y), ldy, gamma, beta, pps, C, G, eps, silu,
+        ws, nblk);
+    count_launch();
+    TC_CHECK_LAUNCH("gn_apply_kernel");
+    return TC_OK;
+}
+
+extern "C" int tc_layernorm(const void* x, long long ldx, void* y, long long ldy, const float* gamma,
+                            const float* beta, int rows, int C, float eps, void* stream_v) {
+    using namespace tc_host;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    TC_CHECK_ARG(x && y && gamma && beta, "tc_layernorm: null pointer");
+    TC_CHECK_ARG(C > 0 && C % 8 == 0 && C <= 2048, "tc_layernorm: need C % 8 == 0 and C <= 2048");
+    TC_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && rows > 0, "tc_layernorm: bad strides/rows");
+    const int threads = 256;
+    const int blocks = (rows + 7) / 8;
+    const __half* xp = reinterpret_cast<const __half*>(x);
+    __half* yp = reinterpret_cast<__half*>(y);
+    if (C <= 512)
+        layernorm_kernel<2><<<blocks, threads, 0, stream>>>(xp, ldx, yp, ldy, gamma, beta, rows, C, eps);
+    else if (C <= 1280)
+        layernorm_kernel<5><<<blocks, threads, 0, stream>>>(xp, ldx, yp, ldy, gamma, beta, rows, C, eps);
+    else
+        layernorm_kernel<8><<<blocks, threads, 0, stream>>>(xp, ldx, yp, ldy, gamma, beta, rows, C, eps);
+    count_launch();
+    TC_CHECK_LAUNCH("layernorm_kernel");
+    return TC_OK;
+}
