@@ -40,6 +40,11 @@ def _pack_conv_w(w):
 @pytest.fixture(scope="module")
 def ops():
     from tooncrafter_b200 import ops as _ops
+    # first cuDNN/cuBLAS use on a fresh box pages in ~1 GB of libraries: do it outside the per-test timeouts
+    F.conv2d(torch.zeros(1, 8, 8, 8, device=DEV), torch.zeros(8, 8, 3, 3, device=DEV), padding=1)
+    F.conv3d(torch.zeros(1, 8, 4, 8, 8, device=DEV), torch.zeros(8, 8, 3, 1, 1, device=DEV), padding=(1, 0, 0))
+    (torch.zeros(8, 8, device=DEV) @ torch.zeros(8, 8, device=DEV)).sum().item()
+    torch.cuda.synchronize()
     return _ops
 
 
@@ -49,11 +54,13 @@ def test_linear_bias_residual(ops, rows, K, N):
     x = _rand(rows, K, seed=1).half()
     w = _rand(N, K, scale=K ** -0.5, seed=2).half()
     bias = _rand(N, seed=3).float()
-    res = _rand(rows, N, seed=4).half()
-    out = torch.zeros(rows, N, dtype=torch.float16, device=DEV)
-    ops.linear(x, w, out, rows=rows, K=K, n_cols=N, bias=bias, res=res)
-    ref = x.float() @ w.float().t() + bias + res.float()
-    _close(out, ref, f"linear {rows}x{K}x{N}")
+    ld = (N + 7) // 8 * 8                      # row strides must be multiples of 8 halfs (16-byte stores)
+    res = _rand(rows, ld, seed=4).half()
+    out = torch.zeros(rows, ld, dtype=torch.float16, device=DEV)
+    ops.linear(x, w, out, rows=rows, K=K, n_cols=N, bias=bias, res=res, ldc=ld, ldr=ld)
+    ref = x.float() @ w.float().t() + bias + res[:, :N].float()
+    _close(out[:, :N], ref, f"linear {rows}x{K}x{N}")
+    assert (out[:, N:] == 0).all()
 
 
 def test_linear_strided_slices(ops):
@@ -93,11 +100,12 @@ def test_conv3x3(ops, N, H, W, Cin, Cout):
     x = _rand(N, H, W, Cin, seed=11).half()            # channels-last
     w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=12)
     bias = _rand(Cout, seed=13).float()
-    out = torch.zeros(N, H, W, Cout, dtype=torch.float16, device=DEV)
+    ld = (Cout + 7) // 8 * 8
+    out = torch.zeros(N, H, W, ld, dtype=torch.float16, device=DEV)
     ops.conv_gemm(x, (N, H, W, Cin), (H * W * Cin, W * Cin, Cin), _pack_conv_w(w), ops.TAPS_3x3, out, (N, H, W),
-                  Cout, bias=bias)
+                  Cout, bias=bias, ldc=ld)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), bias, padding=1).permute(0, 2, 3, 1)
-    _close(out, ref, f"conv3x3 {N}x{H}x{W} {Cin}->{Cout}")
+    _close(out[..., :Cout], ref, f"conv3x3 {N}x{H}x{W} {Cin}->{Cout}")
 
 
 def test_conv3x3_emb_bias_and_skip(ops):
