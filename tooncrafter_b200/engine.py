@@ -147,11 +147,14 @@ def feed_forward(bld: Builder, x: Act, p: _P, out: Act):
 
 # ------------------------------------------------------------------------------------------------ the UNet engine
 class UNetEngine:
-    def __init__(self, unet: nn.Module, device=None, arena_bytes: int = 0, use_graph: bool = True):
+    def __init__(self, unet: nn.Module, device=None, arena_bytes: int = 0, use_graph: bool = True,
+                 plan_only: bool = False):
+        """plan_only=True builds programs without a GPU (host-logic tests interpret them); it cannot execute."""
         self.lay: UNetLayout = unet.layout
         p0 = next(unet.parameters())
-        self.dev = device if device is not None else p0.device
-        if self.dev.type != "cuda":
+        self.dev = torch.device(device) if device is not None else p0.device
+        self.plan_only = plan_only
+        if self.dev.type != "cuda" and not plan_only:
             raise RuntimeError("tooncrafter_b200 runs on CUDA only (no CPU fallback); move the model to a GPU")
         self._sig = (p0.data_ptr(), p0._version)
         self.use_graph = use_graph
@@ -513,19 +516,28 @@ class UNetEngine:
         main.add(ops.ncthw_to_cl, plan.x_in, x0_t, B=B, C_=lay.in_channels, T=T, H=H, W=W, Cpad=cpad, coff=0,
                  scale=1.0)
 
+        plan.marks = []        # (launch count, name, Act): block boundaries, for debugging / tests
+
+        def mark(name, a):
+            plan.marks.append((len(main), name, a))
+
         nin = len(self.p_input)
         h = x0
         for j in range(nin):
             if j == 0 and self.p_init:
                 h = run_layers(self.p_input[0], h, None)
+                mark("conv_in", h)
                 h = run_layers(self.p_init, h, skip_dst(0))
             else:
                 h = run_layers(self.p_input[j], h, skip_dst(j))
+            mark(f"input_blocks.{j}", h)
         h = run_layers(self.p_middle, h, head_dst(0))
+        mark("middle_block", h)
         nout = len(self.p_output)
         for k in range(nout):
             dst = head_dst(k + 1) if k + 1 < nout else None
             h = run_layers(self.p_output[k], cats[k], dst)
+            mark(f"output_blocks.{k}", h)
         for c in cats:
             pass           # concat buffers stay allocated for the life of the plan (static program)
         # --- out: GN + SiLU + conv3x3 -> NCTHW fp16
@@ -544,21 +556,18 @@ class UNetEngine:
             self._plans[key] = self._build(B, T, H, W, n_ctx)
         return self._plans[key]
 
-    def set_context(self, plan, context: torch.Tensor) -> None:
+    def set_context(self, plan, context: torch.Tensor, executor=None) -> None:
         key = (context.data_ptr(), context._version, tuple(context.shape))
         if plan.ctx_key == key:
             return
         B, T = plan.B, plan.T
         plan.ctx_txt.copy_(context[:, :77].reshape(B * 77, -1))
         plan.ctx_img.copy_(context[:, 77:].reshape(B * T * 16, -1))
-        plan.ctx.run()
+        plan.ctx.run(executor)
         plan.ctx_key = key
 
-    @torch.no_grad()
-    def forward(self, x: torch.Tensor, timesteps: torch.Tensor, context: torch.Tensor, fs=None) -> torch.Tensor:
-        B, _, T, H, W = x.shape
-        plan = self.plan_for(B, T, H, W, context.shape[1])
-        self.set_context(plan, context)
+    def load_inputs(self, plan, x, timesteps, fs) -> None:
+        B = plan.B
         plan.x_in.copy_(x)
         plan.t_in.copy_(timesteps.to(torch.float32))
         if self.lay.fs_condition:
@@ -566,5 +575,19 @@ class UNetEngine:
                 plan.fs_in.fill_(float(self.lay.default_fs))
             else:
                 plan.fs_in.copy_(torch.as_tensor(fs, device=self.dev).to(torch.float32).reshape(-1).expand(B))
-        plan.main.replay(self.use_graph)
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, timesteps: torch.Tensor, context: torch.Tensor, fs=None,
+                executor=None) -> torch.Tensor:
+        """`executor` (tests only) interprets the recorded program instead of launching it."""
+        if self.plan_only and executor is None:
+            raise RuntimeError("plan_only engine cannot execute")
+        B, _, T, H, W = x.shape
+        plan = self.plan_for(B, T, H, W, context.shape[1])
+        self.set_context(plan, context, executor)
+        self.load_inputs(plan, x, timesteps, fs)
+        if executor is not None:
+            plan.main.run(executor)
+        else:
+            plan.main.replay(self.use_graph)
         return plan.y_out

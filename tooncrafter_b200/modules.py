@@ -29,6 +29,9 @@ class Node(nn.Module):
         self.add_module(str(name), module)
         return module
 
+    def __getitem__(self, idx):
+        return getattr(self, str(idx))
+
 
 def _numbered(entries: dict) -> Node:
     n = Node()

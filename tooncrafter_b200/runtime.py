@@ -90,7 +90,8 @@ class Act:
     def as_torch(self) -> torch.Tensor:
         """[N, H, W, C] strided torch view (debug / tests only)."""
         return torch.as_strided(self.t, (self.N, self.H, self.W, self.C), (self.H * self.W * self.ld, self.W * self.ld,
-                                                                         self.ld, 1), self.off)
+                                                                         self.ld, 1),
+                                self.t.storage_offset() + self.off)
 
 
 class Program:
@@ -103,7 +104,12 @@ class Program:
     def add(self, fn: Callable, *args, **kw) -> None:
         self.calls.append((fn, args, kw))
 
-    def run(self) -> None:
+    def run(self, executor: Optional[Callable] = None) -> None:
+        """Issue every recorded launch; `executor(fn, args, kw)` lets tests interpret the program instead."""
+        if executor is not None:
+            for fn, args, kw in self.calls:
+                executor(fn, args, kw)
+            return
         for fn, args, kw in self.calls:
             fn(*args, **kw)
 
