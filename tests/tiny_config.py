@@ -17,7 +17,7 @@ TINY_UNET = dict(
     use_causal_attention=False, temporal_length=TINY_T, addition_attention=True, image_cross_attention=True,
     default_fs=24, fs_condition=True)
 
-TINY_DDCONFIG = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=32,
+TINY_DDCONFIG = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=64,
                      ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0)
 
 FULL_UNET = dict(

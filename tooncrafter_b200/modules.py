@@ -179,7 +179,7 @@ class UNetModel(nn.Module):
         from .engine import UNetEngine
         if self._engine is None or not self._engine.matches(self):
             self._engine = UNetEngine(self)
-        return self._engine.forward(x, timesteps, context, fs)
+        return self._engine.forward(x, timesteps, context, fs).clone()
 
 
 # ----------------------------------------------------------------------------------------------------- VAE parts

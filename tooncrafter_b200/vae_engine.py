@@ -1,0 +1,483 @@
+"""CUDA execution engine for the dual-reference video decoder (AutoencoderKL_Dualref / VideoDecoder).
+
+Reference semantics restated (paths relative to /root/reference):
+  Decoder.forward                     lvdm/models/autoencoder_dualref.py:489-527
+  VideoResBlock / ResnetBlock / 3-D ResBlock (skip_t_emb)         :72-92, 672-698, 892-911
+  MemoryEfficientAttnBlock (mid, 1 head, d = C)                   :172-206
+  MemoryEfficientCrossAttentionWrapperFusion (levels 2, 3)        :270-341
+  Combiner (levels 0, 1 and before conv_out)                      :357-368
+  AE3DConv (conv_out + time_mix_conv)                             :929-935
+  AutoencoderKL.decode skips post_quant_conv when kwargs are given  lvdm/models/autoencoder.py:112-116
+One call decodes ONE chunk of T latents of ONE clip (the only case in which the reference is well defined,
+SURVEY App. C.2/C.3); the T = 16 and T = 14 passes of scripts/evaluation/inference.py:262-270 use two plans.
+
+B200-first notes: the learned alpha-blend of VideoResBlock is folded into the last temporal conv's epilogue
+(out = s + sigmoid(mix) * h), the Combiner's add is the residual of its own 1x1-conv GEMM written in place,
+reference-frame K/V projections are computed once per clip, and the mid-block softmax bias trick
+(P (V + 1 b^T) = P V + b^T) lets V^T be produced directly by a GEMM.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .engine import _P, _f, _h, gemm, groupnorm, linear, pack_conv, pack_linear, pack_norm, temporal_conv
+from .layout import DecoderLayout
+from .runtime import Act, Arena, Builder, Program
+
+
+class DecoderEngine:
+    def __init__(self, decoder: nn.Module, device=None, arena_bytes: int = 0, use_graph: bool = True,
+                 plan_only: bool = False):
+        self.lay: DecoderLayout = decoder.layout
+        p0 = next(decoder.parameters())
+        self.dev = torch.device(device) if device is not None else p0.device
+        self.plan_only = plan_only
+        if self.dev.type != "cuda" and not plan_only:
+            raise RuntimeError("tooncrafter_b200 runs on CUDA only (no CPU fallback); move the model to a GPU")
+        self._sig = (p0.data_ptr(), p0._version)
+        self.use_graph = use_graph
+        self.arena_bytes = arena_bytes
+        self._pack(decoder)
+        self._plans: Dict = {}
+
+    def matches(self, decoder) -> bool:
+        p0 = next(decoder.parameters())
+        return self._sig == (p0.data_ptr(), p0._version) and p0.device == self.dev
+
+    # ---------------------------------------------------------------------------------- packing
+    def _pack(self, d: nn.Module):
+        dev, lay = self.dev, self.lay
+
+        def res(m):
+            cin, cout = m.conv1.weight.shape[1], m.conv1.weight.shape[0]
+            p = _P(cin=cin, cout=cout)
+            p.n1, p.n2 = pack_norm(m.norm1, dev), pack_norm(m.norm2, dev)
+            p.c1_w, p.c1_b = pack_conv(m.conv1.weight, dev), _f(m.conv1.bias, dev)
+            p.c2_w, p.c2_b = pack_conv(m.conv2.weight, dev), _f(m.conv2.bias, dev)
+            if hasattr(m, "nin_shortcut"):
+                p.nin_w, p.nin_b = pack_linear(m.nin_shortcut.weight, dev), _f(m.nin_shortcut.bias, dev)
+            else:
+                p.nin_w = None
+            ts = m.time_stack
+            p.tn1, p.tn2 = pack_norm(ts.in_layers[0], dev), pack_norm(ts.out_layers[0], dev)
+            p.t1_w, p.t1_b = pack_conv(ts.in_layers[2].weight, dev), _f(ts.in_layers[2].bias, dev)
+            p.t2_w, p.t2_b = pack_conv(ts.out_layers[3].weight, dev), _f(ts.out_layers[3].bias, dev)
+            p.alpha = float(torch.sigmoid(m.mix_factor.detach().float()).item())
+            return p
+
+        self.cpad_in = (lay.z_channels + 63) // 64 * 64
+        self.p_conv_in = _P(w=pack_conv(d.conv_in.weight, dev, self.cpad_in), b=_f(d.conv_in.bias, dev))
+        self.p_mid1, self.p_mid2 = res(d.mid.block_1), res(d.mid.block_2)
+        a = d.mid.attn_1
+        C = lay.block_in
+        self.p_attn = _P(C=C, norm=pack_norm(a.norm, dev),
+                         qk_w=_h(torch.cat([a.q.weight.reshape(C, C), a.k.weight.reshape(C, C)], 0), dev),
+                         qk_b=_f(torch.cat([a.q.bias, a.k.bias], 0), dev),
+                         v_w=pack_linear(a.v.weight, dev), v_b=_f(a.v.bias, dev),
+                         o_w=pack_linear(a.proj_out.weight, dev), o_b=_f(a.proj_out.bias, dev))
+        self.p_levels: List[_P] = []
+        for i, lv in enumerate(lay.levels):
+            up = d.up[i]
+            p = _P(channels=lv["channels"], refine=lv["refine"], upsample=lv["upsample"])
+            p.blocks = [res(up.block[j]) for j in range(len(lv["blocks"]))]
+            r = d.attn_refinement[i]
+            if lv["refine"] == "fusion":
+                heads = r.to_q.weight.shape[0] // 64
+                p.fus = _P(heads=heads, norm=pack_norm(r.norm, dev), q_w=pack_linear(r.to_q.weight, dev),
+                           kv_w=_h(torch.cat([r.to_k.weight, r.to_v.weight], 0), dev),
+                           o_w=pack_linear(r.to_out[0].weight, dev), o_b=_f(r.to_out[0].bias, dev))
+            else:
+                p.comb = _P(w=pack_linear(r.conv.weight, dev), b=_f(r.conv.bias, dev))
+            if lv["upsample"]:
+                p.up_w, p.up_b = pack_conv(up.upsample.conv.weight, dev), _f(up.upsample.conv.bias, dev)
+            self.p_levels.append(p)
+        rf = d.attn_refinement[lay.num_resolutions]
+        self.p_final = _P(norm=pack_norm(d.norm_out, dev), comb_w=pack_linear(rf.conv.weight, dev),
+                          comb_b=_f(rf.conv.bias, dev), out_w=pack_conv(d.conv_out.weight, dev),
+                          out_b=_f(d.conv_out.bias, dev),
+                          tmix_w=pack_conv(d.conv_out.time_mix_conv.weight, dev, 64),
+                          tmix_b=_f(d.conv_out.time_mix_conv.bias, dev))
+
+    # ---------------------------------------------------------------------------------- builders
+    def _video_res(self, bld: Builder, p: _P, x: Act, dst: Act, T: int) -> None:
+        N, H, W = x.N, x.H, x.W
+        g1 = bld.act(N, H, W, p.cin)
+        groupnorm(bld, x, g1, p.n1, silu=True)
+        h1 = bld.act(N, H, W, p.cout)
+        gemm(bld, g1, p.c1_w, ops.TAPS_3x3, h1, bias=p.c1_b)
+        g1.free()
+        g2 = bld.act(N, H, W, p.cout)
+        groupnorm(bld, h1, g2, p.n2, silu=True)
+        h1.free()
+        if p.nin_w is not None:
+            xs = bld.act(N, H, W, p.cout)
+            linear(bld, x, p.nin_w, xs, bias=p.nin_b)
+        else:
+            xs = x
+        s = bld.act(N, H, W, p.cout)
+        gemm(bld, g2, p.c2_w, ops.TAPS_3x3, s, bias=p.c2_b, res=xs)
+        g2.free()
+        if xs is not x:
+            xs.free()
+        # time stack: GN (stats over all T frames) -> SiLU -> conv (3,1,1), twice; alpha blend in the epilogue
+        g3 = bld.act(N, H, W, p.cout)
+        groupnorm(bld, s, g3, p.tn1, frames_per_stat=T, silu=True)
+        h3 = bld.act(N, H, W, p.cout)
+        temporal_conv(bld, g3, p.t1_w, h3, 1, bias=p.t1_b)
+        g3.free()
+        g4 = bld.act(N, H, W, p.cout)
+        groupnorm(bld, h3, g4, p.tn2, frames_per_stat=T, silu=True)
+        h3.free()
+        temporal_conv(bld, g4, p.t2_w, dst, 1, bias=p.t2_b, res=s, acc_scale=p.alpha)
+        g4.free()
+        s.free()
+
+    def _mid_attention(self, bld: Builder, p: _P, x: Act, dst: Act) -> None:   # also used by EncoderEngine (self unused)
+        N, H, W, C = x.N, x.H, x.W, p.C
+        L = H * W
+        n = bld.act(N, H, W, C)
+        groupnorm(bld, x, n, p.norm)
+        qk = bld.act(N, H, W, 2 * C)
+        linear(bld, n, p.qk_w, qk, bias=p.qk_b)
+        scale = C ** -0.5
+        S_t, S_off = bld.raw(N * L * L)
+        vt_t, vt_off = bld.raw(N * C * L)
+        att = bld.act(N, H, W, C)
+        for f in range(N):
+            q_f = Act(qk.t, 1, 1, L, C, 2 * C, f * L * 2 * C)
+            k_f = torch.as_strided(qk.t, (L, C), (2 * C, 1), qk.t.storage_offset() + f * L * 2 * C + C)
+            S_f = Act(S_t, 1, 1, L, L, L, f * L * L)
+            # S = (Q K^T) / sqrt(C): scale folded into the epilogue so fp16 scores stay small
+            linear(bld, q_f, k_f, S_f, acc_scale=scale)
+            # V0^T = Wv n_f^T  (bias added after the softmax-weighted sum, rows of P sum to 1)
+            wv = Act(p.v_w, 1, 1, C, C, C)
+            n_f = torch.as_strided(n.t, (L, C), (C, 1), n.t.storage_offset() + f * L * C)
+            linear(bld, wv, n_f, Act(vt_t, 1, 1, C, L, L, f * C * L))
+        bld.op(ops.softmax_rows, S_t, rows=N * L, cols=L, scale=1.0)
+        n.free()
+        qk.free()
+        for f in range(N):
+            P_f = Act(S_t, 1, 1, L, L, L, f * L * L)
+            vt_f = torch.as_strided(vt_t, (C, L), (L, 1), vt_t.storage_offset() + f * C * L)
+            linear(bld, P_f, vt_f, Act(att.t, 1, 1, L, C, C, f * L * C), bias=p.v_b)
+        bld.free_raw(S_off)
+        bld.free_raw(vt_off)
+        linear(bld, att, p.o_w, dst, bias=p.o_b, res=x)
+        att.free()
+
+    def _fusion(self, bld: Builder, p: _P, x: Act, dst: Act, kv: torch.Tensor, n_kv: int) -> None:
+        N, H, W, C = x.N, x.H, x.W, x.C
+        n = bld.act(N, H, W, C)
+        groupnorm(bld, x, n, p.norm)
+        inner = p.heads * 64
+        q = bld.act(N, H, W, inner)
+        linear(bld, n, p.q_w, q)
+        n.free()
+        att = bld.act(N, H, W, inner)
+        bld.op(ops.attention, q.t, [dict(k=kv, v=kv, ldk=2 * inner, ldv=2 * inner, Lk=n_kv, kv_div=N, v_offset=inner)],
+               att.t, q_batches=N, Lq=H * W, heads=p.heads, scale=64 ** -0.5, ldq=inner, ldo=inner)
+        q.free()
+        linear(bld, att, p.o_w, dst, bias=p.o_b, res=x)
+        att.free()
+
+    @staticmethod
+    def _combine(bld: Builder, w, b, x: Act, ctx_tokens: torch.Tensor, C: int) -> None:
+        """x[frame 0] += conv1x1(ctx[0]); x[frame -1] += conv1x1(ctx[1])  (in place: out aliases the residual)."""
+        HW = x.H * x.W
+        for which, frame in ((0, 0), (1, x.N - 1)):
+            src = Act(ctx_tokens, 1, 1, HW, C, C, which * HW * C)
+            tgt = Act(x.t, 1, 1, HW, x.C, x.ld, x.off + frame * HW * x.ld)
+            linear(bld, src, w, tgt, bias=b, res=tgt)
+
+    # ---------------------------------------------------------------------------------- plan
+    def _build(self, T: int, h: int, w: int):
+        lay, dev = self.lay, self.dev
+        nlev = lay.num_resolutions
+        H0, W0 = h * 2 ** (nlev - 1), w * 2 ** (nlev - 1)
+        biggest = T * H0 * W0 * max(lay.levels[0]["channels"], 2 * lay.levels[0]["channels"]) * 2
+        arena_bytes = self.arena_bytes or int(biggest * 7 + T * (h * w) ** 2 * 2 + (512 << 20))
+        arena = Arena(arena_bytes, dev)
+        main, ctxp = Program(), Program()
+        bld, cb = Builder(arena, main), Builder(arena, ctxp)
+        plan = _P(T=T, h=h, w=w, arena=arena, main=main, ctx=ctxp, ctx_key=None)
+        plan.z_in = torch.zeros(T, lay.z_channels, 1, h, w, dtype=torch.float32, device=dev)   # (frames as batch)
+        z_cl = torch.zeros(T * h * w * self.cpad_in, dtype=torch.float16, device=dev)
+        main.add(ops.ncthw_to_cl, plan.z_in, z_cl, B=T, C_=lay.z_channels, T=1, H=h, W=w, Cpad=self.cpad_in, coff=0,
+                 scale=1.0)
+        # reference-frame context: static NCTHW fp32 inputs -> channels-last tokens (+ fused K/V for fusion levels)
+        plan.ref_in, plan.ref_tok, plan.kv = [], [], {}
+        for i in range(nlev + 1):
+            lv = i if i < nlev else 0
+            c = lay.levels[lv]["channels"] if i < nlev else lay.levels[0]["channels"]
+            hh, ww = (h * 2 ** (nlev - 1 - lv), w * 2 ** (nlev - 1 - lv))
+            rin = torch.zeros(1, c, 2, hh, ww, dtype=torch.float32, device=dev)
+            tok = torch.zeros(2 * hh * ww * c, dtype=torch.float16, device=dev)
+            ctxp.add(ops.ncthw_to_cl, rin, tok, B=1, C_=c, T=2, H=hh, W=ww, Cpad=c, coff=0, scale=1.0)
+            plan.ref_in.append(rin)
+            plan.ref_tok.append(tok)
+            if i < nlev and self.p_levels[i].refine == "fusion":
+                p = self.p_levels[i].fus
+                inner = p.heads * 64
+                kv = torch.zeros(2 * hh * ww, 2 * inner, dtype=torch.float16, device=dev)
+                linear(cb, Act(tok, 1, 1, 2 * hh * ww, c, c), p.kv_w, Act(kv, 1, 1, 2 * hh * ww, 2 * inner, 2 * inner))
+                plan.kv[i] = (kv, 2 * hh * ww)
+
+        x = Act(z_cl, T, h, w, self.cpad_in, self.cpad_in)
+        cur = bld.act(T, h, w, lay.block_in)
+        gemm(bld, x, self.p_conv_in.w, ops.TAPS_3x3, cur, bias=self.p_conv_in.b)
+        plan.marks = []
+
+        nxt = bld.act(T, h, w, lay.block_in)
+        self._video_res(bld, self.p_mid1, cur, nxt, T); cur.free(); cur = nxt
+        nxt = bld.act(T, h, w, lay.block_in)
+        self._mid_attention(bld, self.p_attn, cur, nxt); cur.free(); cur = nxt
+        nxt = bld.act(T, h, w, lay.block_in)
+        self._video_res(bld, self.p_mid2, cur, nxt, T); cur.free(); cur = nxt
+        plan.marks.append((len(main), "mid", cur))
+        for i in reversed(range(nlev)):
+            p = self.p_levels[i]
+            for rb in p.blocks:
+                nxt = bld.act(T, cur.H, cur.W, rb.cout)
+                self._video_res(bld, rb, cur, nxt, T); cur.free(); cur = nxt
+            if p.refine == "fusion":
+                nxt = bld.act(T, cur.H, cur.W, cur.C)
+                kv, n_kv = plan.kv[i]
+                self._fusion(bld, p.fus, cur, nxt, kv, n_kv); cur.free(); cur = nxt
+            else:
+                self._combine(bld, p.comb.w, p.comb.b, cur, plan.ref_tok[i], cur.C)
+            if p.upsample:
+                up = bld.act(T, 2 * cur.H, 2 * cur.W, cur.C)
+                bld.op(ops.upsample2x, cur.t, up.t, N=T, H=cur.H, W=cur.W, C_=cur.C)
+                cur.free()
+                nxt = bld.act(T, up.H, up.W, up.C)
+                gemm(bld, up, p.up_w, ops.TAPS_3x3, nxt, bias=p.up_b)
+                up.free()
+                cur = nxt
+            plan.marks.append((len(main), f"level{i}", cur))
+        pf = self.p_final
+        g = bld.act(T, cur.H, cur.W, cur.C)
+        groupnorm(bld, cur, g, pf.norm, silu=True)
+        cur.free()
+        self._combine(bld, pf.comb_w, pf.comb_b, g, plan.ref_tok[nlev], g.C)
+        # conv_out (C -> out_ch) into a zero-initialised 64-channel buffer, then the (3,1,1) time-mix conv
+        Hf, Wf = g.H, g.W
+        co_t = torch.zeros(T * Hf * Wf * 64, dtype=torch.float16, device=dev)
+        co = Act(co_t, T, Hf, Wf, 64, 64)
+        gemm(bld, g, pf.out_w, ops.TAPS_3x3, co, bias=pf.out_b, n_cols=lay.out_ch)
+        g.free()
+        fin = bld.act(T, Hf, Wf, 16)
+        temporal_conv(bld, co, pf.tmix_w, fin, 1, bias=pf.tmix_b, n_cols=lay.out_ch)
+        plan.y_out = torch.zeros(T, lay.out_ch, 1, Hf, Wf, dtype=torch.float16, device=dev)
+        main.add(ops.cl_to_ncthw, fin.t, plan.y_out, B=T, C_=lay.out_ch, T=1, H=Hf, W=Wf, ldx=16)
+        return plan
+
+    def plan_for(self, T, h, w):
+        key = (T, h, w)
+        if key not in self._plans:
+            self._plans[key] = self._build(T, h, w)
+        return self._plans[key]
+
+    def set_ref_context(self, plan, ref_context, executor=None) -> None:
+        key = tuple((t.data_ptr(), t._version) for t in ref_context)
+        if plan.ctx_key == key:
+            return
+        if len(ref_context) != len(plan.ref_in):
+            raise ValueError(f"ref_context must hold {len(plan.ref_in)} maps")
+        for dst, src in zip(plan.ref_in, ref_context):
+            if tuple(src.shape) != tuple(dst.shape):
+                raise ValueError(f"ref_context map {tuple(src.shape)} != expected {tuple(dst.shape)} "
+                                 "(one clip per decode call: batch must be 1)")
+            dst.copy_(src)
+        plan.ctx.run(executor)
+        plan.ctx_key = key
+
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor, ref_context, executor=None) -> torch.Tensor:
+        """z [T, z_channels, h, w] (already divided by scale_factor), ref_context: 5 maps [1, C, 2, H_l, W_l]
+        -> [T, 3, 8h, 8w] fp16."""
+        if self.plan_only and executor is None:
+            raise RuntimeError("plan_only engine cannot execute")
+        if ref_context is None:
+            raise NotImplementedError("VideoDecoder without ref_context is outside the supported hot path")
+        T, _, h, w = z.shape
+        plan = self.plan_for(T, h, w)
+        self.set_ref_context(plan, ref_context, executor)
+        plan.z_in.copy_(z.reshape(plan.z_in.shape))
+        if executor is not None:
+            plan.main.run(executor)
+        else:
+            plan.main.replay(self.use_graph)
+        return plan.y_out.reshape(T, self.lay.out_ch, plan.y_out.shape[-2], plan.y_out.shape[-1])
+
+
+def taps_3x3_stride2_pad_br(n_frames: int):
+    """3x3 / stride 2 conv after F.pad(x, (0, 1, 0, 1)) (ae_modules.py:104-108) over a phase-split input:
+    input row 2*y + ky  ->  phase row parity ky & 1, row offset ky >> 1."""
+    taps = []
+    for ky in range(3):
+        for kx in range(3):
+            taps.append((kx >> 1, ky >> 1, ((ky & 1) * 2 + (kx & 1)) * n_frames))
+    return taps
+
+
+class EncoderEngine:
+    """AutoencoderKL.encode(x, return_hidden_states=True): Encoder + quant_conv ("next" row).
+
+    Reference: lvdm/modules/networks/ae_modules.py:432-475 (Encoder.forward), :153-213 (ResnetBlock), :28-75
+    (AttnBlock), :92-108 (Downsample, asymmetric pad); lvdm/models/autoencoder.py:100-105 (quant_conv)."""
+
+    def __init__(self, ae: nn.Module, device=None, arena_bytes: int = 0, use_graph: bool = False,
+                 plan_only: bool = False):
+        enc = ae.encoder
+        self.lay = enc.layout
+        p0 = next(enc.parameters())
+        self.dev = torch.device(device) if device is not None else p0.device
+        self.plan_only = plan_only
+        if self.dev.type != "cuda" and not plan_only:
+            raise RuntimeError("tooncrafter_b200 runs on CUDA only (no CPU fallback); move the model to a GPU")
+        self._sig = (p0.data_ptr(), p0._version)
+        self.use_graph = use_graph
+        self.arena_bytes = arena_bytes
+        self._pack(ae)
+        self._plans: Dict = {}
+
+    def matches(self, ae) -> bool:
+        p0 = next(ae.encoder.parameters())
+        return self._sig == (p0.data_ptr(), p0._version) and p0.device == self.dev
+
+    def _pack(self, ae):
+        dev, lay, e = self.dev, self.lay, ae.encoder
+
+        def res(m):
+            cin, cout = m.conv1.weight.shape[1], m.conv1.weight.shape[0]
+            p = _P(cin=cin, cout=cout, n1=pack_norm(m.norm1, dev), n2=pack_norm(m.norm2, dev),
+                   c1_w=pack_conv(m.conv1.weight, dev), c1_b=_f(m.conv1.bias, dev),
+                   c2_w=pack_conv(m.conv2.weight, dev), c2_b=_f(m.conv2.bias, dev), nin_w=None)
+            if hasattr(m, "nin_shortcut"):
+                p.nin_w, p.nin_b = pack_linear(m.nin_shortcut.weight, dev), _f(m.nin_shortcut.bias, dev)
+            return p
+
+        self.cpad_in = (lay.in_channels + 63) // 64 * 64
+        self.p_conv_in = _P(w=pack_conv(e.conv_in.weight, dev, self.cpad_in), b=_f(e.conv_in.bias, dev))
+        self.p_levels = []
+        for i, lv in enumerate(lay.levels):
+            d = e.down[i]
+            p = _P(blocks=[res(d.block[j]) for j in range(len(lv["blocks"]))], down=lv["downsample"],
+                   channels=lv["channels"])
+            if lv["downsample"]:
+                p.down_w, p.down_b = pack_conv(d.downsample.conv.weight, dev), _f(d.downsample.conv.bias, dev)
+            self.p_levels.append(p)
+        self.p_mid1, self.p_mid2 = res(e.mid.block_1), res(e.mid.block_2)
+        a, C = e.mid.attn_1, lay.block_in
+        self.p_attn = _P(C=C, norm=pack_norm(a.norm, dev),
+                         qk_w=_h(torch.cat([a.q.weight.reshape(C, C), a.k.weight.reshape(C, C)], 0), dev),
+                         qk_b=_f(torch.cat([a.q.bias, a.k.bias], 0), dev),
+                         v_w=pack_linear(a.v.weight, dev), v_b=_f(a.v.bias, dev),
+                         o_w=pack_linear(a.proj_out.weight, dev), o_b=_f(a.proj_out.bias, dev))
+        self.zc2 = e.conv_out.weight.shape[0]
+        self.p_out = _P(norm=pack_norm(e.norm_out, dev), w=pack_conv(e.conv_out.weight, dev), b=_f(e.conv_out.bias, dev),
+                        q_w=_h(torch.nn.functional.pad(ae.quant_conv.weight.detach().reshape(ae.quant_conv.weight.shape[0], -1),
+                                                       (0, 64 - self.zc2)), dev),
+                        q_b=_f(ae.quant_conv.bias, dev), q_out=ae.quant_conv.weight.shape[0])
+
+    @staticmethod
+    def _resnet2d(bld: Builder, p: _P, x: Act, dst: Act) -> None:
+        N, H, W = x.N, x.H, x.W
+        g1 = bld.act(N, H, W, p.cin)
+        groupnorm(bld, x, g1, p.n1, silu=True)
+        h1 = bld.act(N, H, W, p.cout)
+        gemm(bld, g1, p.c1_w, ops.TAPS_3x3, h1, bias=p.c1_b)
+        g1.free()
+        g2 = bld.act(N, H, W, p.cout)
+        groupnorm(bld, h1, g2, p.n2, silu=True)
+        h1.free()
+        if p.nin_w is not None:
+            xs = bld.act(N, H, W, p.cout)
+            linear(bld, x, p.nin_w, xs, bias=p.nin_b)
+        else:
+            xs = x
+        gemm(bld, g2, p.c2_w, ops.TAPS_3x3, dst, bias=p.c2_b, res=xs)
+        g2.free()
+        if xs is not x:
+            xs.free()
+
+    def _build(self, N: int, H: int, W: int):
+        lay, dev = self.lay, self.dev
+        biggest = N * H * W * lay.ch * 2
+        arena = Arena(self.arena_bytes or int(biggest * 10 + N * ((H // 8) * (W // 8)) ** 2 * 2 + (256 << 20)), dev)
+        main = Program()
+        bld = Builder(arena, main)
+        plan = _P(N=N, H=H, W=W, arena=arena, main=main)
+        plan.x_in = torch.zeros(N, lay.in_channels, 1, H, W, dtype=torch.float32, device=dev)
+        x_cl = torch.zeros(N * H * W * self.cpad_in, dtype=torch.float16, device=dev)
+        main.add(ops.ncthw_to_cl, plan.x_in, x_cl, B=N, C_=lay.in_channels, T=1, H=H, W=W, Cpad=self.cpad_in, coff=0,
+                 scale=1.0)
+        plan.hidden = []
+
+        def export(a: Act):
+            out = torch.zeros(N, a.C, 1, a.H, a.W, dtype=torch.float16, device=dev)
+            main.add(ops.cl_to_ncthw, a.t, out, B=N, C_=a.C, T=1, H=a.H, W=a.W, ldx=a.ld, x_offset=a.off)
+            return out
+
+        first = bld.act(N, H, W, lay.ch)
+        gemm(bld, Act(x_cl, N, H, W, self.cpad_in, self.cpad_in), self.p_conv_in.w, ops.TAPS_3x3, first,
+             bias=self.p_conv_in.b)
+        first_out = export(first)
+        cur = first
+        for p in self.p_levels:
+            for rb in p.blocks:
+                nxt = bld.act(N, cur.H, cur.W, rb.cout)
+                self._resnet2d(bld, rb, cur, nxt)
+                cur.free()
+                cur = nxt
+            plan.hidden.append(export(cur))
+            if p.down:
+                ph = bld.act(4 * N, cur.H // 2, cur.W // 2, cur.C)
+                bld.op(ops.phase_split2, cur.t, ph.t, N=N, H=cur.H, W=cur.W, C_=cur.C)
+                nxt = bld.act(N, cur.H // 2, cur.W // 2, cur.C)
+                gemm(bld, ph, p.down_w, taps_3x3_stride2_pad_br(N), nxt, bias=p.down_b)
+                ph.free()
+                cur.free()
+                cur = nxt
+        plan.hidden.append(first_out)
+        nxt = bld.act(N, cur.H, cur.W, cur.C)
+        self._resnet2d(bld, self.p_mid1, cur, nxt); cur.free(); cur = nxt
+        nxt = bld.act(N, cur.H, cur.W, cur.C)
+        DecoderEngine._mid_attention(None, bld, self.p_attn, cur, nxt); cur.free(); cur = nxt
+        nxt = bld.act(N, cur.H, cur.W, cur.C)
+        self._resnet2d(bld, self.p_mid2, cur, nxt); cur.free(); cur = nxt
+        g = bld.act(N, cur.H, cur.W, cur.C)
+        groupnorm(bld, cur, g, self.p_out.norm, silu=True)
+        cur.free()
+        co_t = torch.zeros(N * g.H * g.W * 64, dtype=torch.float16, device=dev)
+        co = Act(co_t, N, g.H, g.W, 64, 64)
+        gemm(bld, g, self.p_out.w, ops.TAPS_3x3, co, bias=self.p_out.b, n_cols=self.zc2)
+        g.free()
+        mo = bld.act(N, co.H, co.W, 16)
+        linear(bld, co, self.p_out.q_w, mo, bias=self.p_out.q_b, n_cols=self.p_out.q_out)
+        plan.moments = torch.zeros(N, self.p_out.q_out, 1, co.H, co.W, dtype=torch.float32, device=dev)
+        main.add(ops.cl_to_ncthw, mo.t, plan.moments, B=N, C_=self.p_out.q_out, T=1, H=co.H, W=co.W, ldx=16)
+        return plan
+
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor, executor=None):
+        """x [N, 3, H, W] in [-1, 1] -> (moments [N, 2*embed, H/8, W/8] fp32, [5 hidden maps [N, C, H_l, W_l] fp16])."""
+        if self.plan_only and executor is None:
+            raise RuntimeError("plan_only engine cannot execute")
+        N, _, H, W = x.shape
+        key = (N, H, W)
+        if key not in self._plans:
+            self._plans[key] = self._build(N, H, W)
+        plan = self._plans[key]
+        plan.x_in.copy_(x.reshape(plan.x_in.shape))
+        if executor is not None:
+            plan.main.run(executor)
+        else:
+            plan.main.replay(self.use_graph)
+        sq = lambda t: t.reshape(t.shape[0], t.shape[1], t.shape[3], t.shape[4]).clone()
+        return sq(plan.moments), [sq(h) for h in plan.hidden]
