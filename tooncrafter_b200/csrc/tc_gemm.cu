@@ -8,7 +8,7 @@
 //                                and one 2-D box of the [Cout][taps*C] weight matrix, 128B-swizzled
 //   warp 1      MMA issuer     : tcgen05.mma cta_group::1 kind::f16, M=128 x N=block_n x K=16, fp32 accum in TMEM,
 //                                two accumulator buffers so the epilogue of tile i overlaps the mainloop of i+1
-//   warps 2..5  epilogue       : tcgen05.ld (one output row per thread) -> +bias, +per-sample embedding,
+//   warps 2..9  epilogue       : tcgen05.ld (one output row per thread, two column groups) -> +bias, +embedding,
 //                                *scale, +residual, optional GEGLU -> fp16 -> 16-byte global stores
 //
 // Roofline: tensor-bound (fp16 dense); algorithmic flops = 2 * M * n_cols * taps * C.
@@ -20,7 +20,7 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                          // 64 halfs = one 128-byte swizzle row
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;  // 16 KiB
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM column offset of the second accumulator
 
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         }
         for (int a = 0; a < 2; ++a) {
             tc::mbar_init(&tfull_bar[a], 1);
-            tc::mbar_init(&tempty_bar[a], 4);
+            tc::mbar_init(&tempty_bar[a], 8);
         }
         tc::fence_mbar_init();
     }
@@ -183,13 +183,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
-        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
+        // Two warps per TMEM lane quadrant: "column group" 0 takes the first half of the tile's columns, group 1 the
+        // second half, so 256 threads keep loads/stores in flight.  Each thread owns one output row; the residual
+        // slice of its row is prefetched into registers BEFORE waiting for the accumulator, i.e. it is hidden
+        // behind the tile's own mainloop.
+        const int q = warp & 3;             // TMEM lane quadrant this warp may access
+        const int cg = (warp - 2) >> 2;     // column group 0 / 1
         const int row = q * 32 + lane;
         const int rx = row % p.TW;
         const int ry = (row / p.TW) % p.TH;
         const int rn = row / (p.TW * p.TH);
         const bool geglu = (p.flags & TC_EPI_GEGLU) != 0;
+        const int width = geglu ? (BN >> 1) : BN;                   // output columns per tile
+        const int split = ((width / 16 + 1) / 2) * 16;              // group 0: [0, split), group 1: [split, width)
+        const int c_begin = cg == 0 ? 0 : split;
+        const int c_end = cg == 0 ? split : width;
+        const bool vec_ok = (p.n_cols % 16) == 0;                   // all chunks complete -> 16-byte paths
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -201,88 +211,125 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             const int x = tx * p.TW + rx, y = ty * p.TH + ry, n = tn * p.TN + rn;
             const bool row_ok = (rn < p.TN) && (x < p.oW) && (y < p.oH) && (n < p.oN);
             const long long m = ((long long)n * p.oH + y) * p.oW + x;
+            const __half* rrow = (p.res && row_ok) ? p.res + m * p.ldr + (long long)nt * BN : nullptr;
+
+            // ---- residual prefetch (up to 128 columns = 16 x 16 B per thread)
+            uint4 rres[16];
+            if (rrow && vec_ok) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c = c_begin + j * 8;
+                    if (c < c_end && nt * BN + c < p.n_cols) rres[j] = *reinterpret_cast<const uint4*>(rrow + c);
+                }
+            }
 
             tc::mbar_wait(&tfull_bar[acc], acc_phase);
             tc::tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(q * 32) << 16);
 
             if (!geglu) {
-                __half* orow = p.out + m * p.ldc;
-                const __half* rrow = p.res ? p.res + m * p.ldr : nullptr;
+                __half* orow = p.out + m * p.ldc + (long long)nt * BN;
                 const __half* b2row =
-                    p.bias2 ? p.bias2 + (row_ok ? (m / p.bias2_rows_per) : 0) * p.bias2_ld : nullptr;
-                for (int c = 0; c < BN; c += 16) {
+                    p.bias2 ? p.bias2 + (row_ok ? (m / p.bias2_rows_per) : 0) * p.bias2_ld + (long long)nt * BN : nullptr;
+                const float* brow = p.bias ? p.bias + (long long)nt * BN : nullptr;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c_begin + j * 16;
+                    if (c >= c_end) break;
                     uint32_t r[16];
                     tc::tmem_ld16(taddr + (uint32_t)c, r);
                     tc::tmem_ld_wait();
-                    const int col0 = nt * BN + c;
-                    const int nvalid = p.n_cols - col0;
-                    if (row_ok && nvalid > 0) {
-                        float v[16];
+                    const int nvalid = p.n_cols - (nt * BN + c);
+                    if (!row_ok || nvalid <= 0) continue;
+                    float v[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-                        if (p.bias) {
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                    if (vec_ok) {
+                        if (brow) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (i < nvalid) v[i] += p.bias[col0 + i];
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c) + i);
+                                v[4 * i] += b4.x;
+                                v[4 * i + 1] += b4.y;
+                                v[4 * i + 2] += b4.z;
+                                v[4 * i + 3] += b4.w;
+                            }
                         }
                         if (b2row) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (i < nvalid) v[i] += __half2float(b2row[col0 + i]);
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const uint4 u = __ldg(reinterpret_cast<const uint4*>(b2row + c) + hh);
+                                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float2 f = __half22float2(h2[i]);
+                                    v[hh * 8 + 2 * i] += f.x;
+                                    v[hh * 8 + 2 * i + 1] += f.y;
+                                }
+                            }
                         }
                         if (p.acc_scale != 1.0f) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] *= p.acc_scale;
                         }
                         if (rrow) {
-                            if (nvalid >= 16) {
-                                const uint4 u0 = reinterpret_cast<const uint4*>(rrow + col0)[0];
-                                const uint4 u1 = reinterpret_cast<const uint4*>(rrow + col0)[1];
-                                const __half2* h0 = reinterpret_cast<const __half2*>(&u0);
-                                const __half2* h1 = reinterpret_cast<const __half2*>(&u1);
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const __half2* h2 = reinterpret_cast<const __half2*>(&rres[2 * j + hh]);
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
-                                    const float2 f0 = __half22float2(h0[i]);
-                                    const float2 f1 = __half22float2(h1[i]);
-                                    v[2 * i] += f0.x;
-                                    v[2 * i + 1] += f0.y;
-                                    v[8 + 2 * i] += f1.x;
-                                    v[8 + 2 * i + 1] += f1.y;
+                                    const float2 f = __half22float2(h2[i]);
+                                    v[hh * 8 + 2 * i] += f.x;
+                                    v[hh * 8 + 2 * i + 1] += f.y;
                                 }
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i)
-                                    if (i < nvalid) v[i] += __half2float(rrow[col0 + i]);
                             }
                         }
-                        store_row16(orow + col0, v, nvalid);
+                        store_row16(orow + c, v, 16);
+                    } else {
+                        // generic path for narrow outputs (n_cols = 3, 4, 8 ...): scalar loads / stores
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            if (i < nvalid) {
+                                if (brow) v[i] += brow[c + i];
+                                if (b2row) v[i] += __half2float(b2row[c + i]);
+                                v[i] *= p.acc_scale;
+                                if (rrow) v[i] += __half2float(rrow[c + i]);
+                            }
+                        }
+                        store_row16(orow + c, v, nvalid);
                     }
                 }
             } else {
-                // weight rows of this N tile are [a-half (BN/2) | gate-half (BN/2)]; output tile is BN/2 wide
+                // weight rows of this N tile are [value half (BN/2) | gate half (BN/2)]; output tile is BN/2 wide
                 const int half_bn = BN >> 1;
                 __half* orow = p.out + m * p.ldc + (long long)nt * half_bn;
-                for (int c = 0; c < half_bn; c += 16) {
+                const float* brow = p.bias ? p.bias + (long long)nt * BN : nullptr;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c_begin + j * 16;
+                    if (c >= c_end) break;
                     uint32_t ra[16], rg[16];
                     tc::tmem_ld16(taddr + (uint32_t)c, ra);
                     tc::tmem_ld16(taddr + (uint32_t)(half_bn + c), rg);
                     tc::tmem_ld_wait();
-                    if (row_ok) {
-                        float v[16];
-                        const int ca = nt * BN + c, cg = nt * BN + half_bn + c;
+                    if (!row_ok) continue;
+                    float v[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float a = __uint_as_float(ra[i]);
-                            float g = __uint_as_float(rg[i]);
-                            if (p.bias) {
-                                a += p.bias[ca + i];
-                                g += p.bias[cg + i];
-                            }
-                            v[i] = a * tc::gelu_erf_f(g);
+                    for (int i = 0; i < 4; ++i) {
+                        float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+                        if (brow) {
+                            ba = __ldg(reinterpret_cast<const float4*>(brow + c) + i);
+                            bg = __ldg(reinterpret_cast<const float4*>(brow + half_bn + c) + i);
                         }
-                        store_row16(orow + c, v, 16);
+                        v[4 * i] = (__uint_as_float(ra[4 * i]) + ba.x) * tc::gelu_erf_f(__uint_as_float(rg[4 * i]) + bg.x);
+                        v[4 * i + 1] =
+                            (__uint_as_float(ra[4 * i + 1]) + ba.y) * tc::gelu_erf_f(__uint_as_float(rg[4 * i + 1]) + bg.y);
+                        v[4 * i + 2] =
+                            (__uint_as_float(ra[4 * i + 2]) + ba.z) * tc::gelu_erf_f(__uint_as_float(rg[4 * i + 2]) + bg.z);
+                        v[4 * i + 3] =
+                            (__uint_as_float(ra[4 * i + 3]) + ba.w) * tc::gelu_erf_f(__uint_as_float(rg[4 * i + 3]) + bg.w);
                     }
+                    store_row16(orow + c, v, 16);
                 }
             }
             tc::tc_fence_before();

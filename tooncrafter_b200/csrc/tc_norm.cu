@@ -51,15 +51,26 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ldx, lon
 #pragma unroll
     for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
     const __half* base = x + (long long)s * pixels_per_stat * ldx + (long long)v * 8;
-    for (long long pix = (long long)blockIdx.x * rows_per_iter + prow; pix < pixels_per_stat;
-         pix += (long long)gridDim.x * rows_per_iter) {
-        const uint4 u = *reinterpret_cast<const uint4*>(base + pix * ldx);
-        float f[8];
-        unpack8(u, f);
+    const long long stride = (long long)gridDim.x * rows_per_iter;
+    // 4 independent 16-byte loads in flight per thread (the pass is pure HBM/L2 streaming)
+    for (long long pix = (long long)blockIdx.x * rows_per_iter + prow; pix < pixels_per_stat; pix += 4 * stride) {
+        uint4 u[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            sum[i] += f[i];
-            sq[i] += f[i] * f[i];
+        for (int k = 0; k < 4; ++k) {
+            const long long pp = pix + k * stride;
+            if (pp < pixels_per_stat) u[k] = *reinterpret_cast<const uint4*>(base + pp * ldx);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (pix + k * stride < pixels_per_stat) {
+                float f[8];
+                unpack8(u[k], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    sum[i] += f[i];
+                    sq[i] += f[i] * f[i];
+                }
+            }
         }
     }
 #pragma unroll
@@ -131,18 +142,29 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, long long ldx, __h
     }
     const __half* xb = x + (long long)s * pixels_per_stat * ldx + (long long)v * 8;
     __half* yb = y + (long long)s * pixels_per_stat * ldy + (long long)v * 8;
-    for (long long pix = (long long)blockIdx.x * rows_per_iter + prow; pix < pixels_per_stat;
-         pix += (long long)gridDim.x * rows_per_iter) {
-        const uint4 u = *reinterpret_cast<const uint4*>(xb + pix * ldx);
-        float f[8];
-        unpack8(u, f);
+    const long long stride = (long long)gridDim.x * rows_per_iter;
+    for (long long pix = (long long)blockIdx.x * rows_per_iter + prow; pix < pixels_per_stat; pix += 4 * stride) {
+        uint4 u[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float t = f[i] * sc[i] + sh[i];
-            if (silu) t = tc::silu_f(t);
-            f[i] = t;
+        for (int k = 0; k < 4; ++k) {
+            const long long pp = pix + k * stride;
+            if (pp < pixels_per_stat) u[k] = *reinterpret_cast<const uint4*>(xb + pp * ldx);
         }
-        *reinterpret_cast<uint4*>(yb + pix * ldy) = pack8(f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long pp = pix + k * stride;
+            if (pp < pixels_per_stat) {
+                float f[8];
+                unpack8(u[k], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float t = f[i] * sc[i] + sh[i];
+                    if (silu) t = tc::silu_f(t);
+                    f[i] = t;
+                }
+                *reinterpret_cast<uint4*>(yb + pp * ldy) = pack8(f);
+            }
+        }
     }
 }
 
@@ -222,7 +244,7 @@ extern "C" int tc_groupnorm(const void* x, long long ldx, void* y, long long ldy
     if (k < 1) k = 1;
     const int threads = V * k;
     // each thread should see >= 8 pixels in the statistics pass; cap partial blocks per stat group
-    long long want = (pps + (long long)k * 8 - 1) / ((long long)k * 8);
+    long long want = (pps + (long long)k * 16 - 1) / ((long long)k * 16);
     int nblk = (int)(want < 1 ? 1 : want);
     int cap = (2 * sm_count() + n_stat - 1) / n_stat;
     if (cap < 1) cap = 1;
@@ -232,7 +254,7 @@ extern "C" int tc_groupnorm(const void* x, long long ldx, void* y, long long ldy
         reinterpret_cast<const __half*>(x), ldx, pps, C, G, ws);
     count_launch();
     TC_CHECK_LAUNCH("gn_stats_kernel");
-    long long want2 = (pps + (long long)k * 4 - 1) / ((long long)k * 4);
+    long long want2 = (pps + (long long)k * 8 - 1) / ((long long)k * 8);
     int nblk2 = (int)(want2 < 1 ? 1 : want2);
     int cap2 = (8 * sm_count() + n_stat - 1) / n_stat;
     if (nblk2 > cap2) nblk2 = cap2;
