@@ -186,6 +186,12 @@ def gemm_roofline(model, dev):
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm
+def cpu_threads():
+    """Host threads for the CPU arm: all cores up to 32 (beyond that the fp32 conv/GEMM mix of this UNet stops
+    scaling and oversubscribed boxes get slower: 128 threads measured 185 s/forward vs 35 s on 8 dedicated cores)."""
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
 def cpu_unet_forward_seconds(threads):
     """Reference algorithm (oracle port, fp32) on the host cores: ONE full-size UNet forward, B = 1."""
     from oracle import unet_oracle
@@ -213,7 +219,7 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     S = args.ddim_steps
     times = []
     for i in range(args.warmup + args.steps):
@@ -367,7 +373,7 @@ def main():
                      "share_of_unet_forward": roof["gemm_ms_per_forward"]},
     }
     if not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = cpu_threads()
         t_fwd = cpu_unet_forward_seconds(cores)
         out["cpu_baseline"] = {"value": 16.0 / (t_fwd * clip_tflop(S) / UNET_TF), "unit": "frames/s", "cores": cores,
                                "kind": "port",

@@ -136,11 +136,15 @@ def test_vae_encoder_and_decoder_engines_match_reference_golden(tiny_ae):
     gi = golden_inputs()
     frames = gi["frames"].to(DEV)
     post, hidden = tiny_ae.encode(frames, return_hidden_states=True)
-    _report("encoder moments", post.parameters, torch.from_numpy(GOLD["enc_moments"]))
     sd = {"first_stage_model." + k: v for k, v in tiny_ae.state_dict().items()}
-    _, hid32 = vae_oracle.encode_hidden(sd, layout.encoder_layout(TINY_DDCONFIG), frames)
+    qw, qb = sd["first_stage_model.quant_conv.weight"], sd["first_stage_model.quant_conv.bias"]
+    h32, hid32 = vae_oracle.encode_hidden(sd, layout.encoder_layout(TINY_DDCONFIG), frames)
     with torch.autocast("cuda", dtype=torch.float16):
-        _, hid16 = vae_oracle.encode_hidden(sd, layout.encoder_layout(TINY_DDCONFIG), frames)
+        h16, hid16 = vae_oracle.encode_hidden(sd, layout.encoder_layout(TINY_DDCONFIG), frames)
+        m16 = torch.nn.functional.conv2d(h16, qw, qb)
+    m32 = torch.nn.functional.conv2d(h32, qw, qb)
+    assert (m32.cpu() - torch.from_numpy(GOLD["enc_moments"])).abs().max().item() < 1e-3
+    _report("encoder moments", post.parameters, torch.from_numpy(GOLD["enc_moments"]), m16)
     for i, h in enumerate(hidden):
         assert (hid32[i].flatten()[::97].cpu() - torch.from_numpy(GOLD[f"enc_hidden{i}_sub"])).abs().max() < 1e-3
         _report(f"encoder hidden {i}", h, hid32[i], hid16[i])

@@ -38,14 +38,12 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // grid = (nblk, n_stat); block = V * k threads (V = C/8), thread t owns channel vector t % V.
 __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ldx, long long pixels_per_stat, int C, int G,
                                 float* __restrict__ partials) {
-    extern __shared__ float sm[];  // [2*C]
+    extern __shared__ float sm[];  // [rows_per_iter][2*C]: per-thread partials, reduced in a fixed order (deterministic)
     const int V = C >> 3;
     const int v = threadIdx.x % V;
     const int prow = threadIdx.x / V;
     const int rows_per_iter = blockDim.x / V;
     const int s = blockIdx.y;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
 
     float sum[8], sq[8];
 #pragma unroll
@@ -73,18 +71,22 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ldx, lon
             }
         }
     }
+    float* mine = sm + (long long)prow * 2 * C;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        atomicAdd(&sm[v * 8 + i], sum[i]);
-        atomicAdd(&sm[C + v * 8 + i], sq[i]);
+        mine[v * 8 + i] = sum[i];
+        mine[C + v * 8 + i] = sq[i];
     }
     __syncthreads();
     const int cpg = C / G;
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         float a = 0.f, b = 0.f;
-        for (int c = 0; c < cpg; ++c) {
-            a += sm[g * cpg + c];
-            b += sm[C + g * cpg + c];
+        for (int r = 0; r < rows_per_iter; ++r) {
+            const float* src = sm + (long long)r * 2 * C;
+            for (int c = 0; c < cpg; ++c) {
+                a += src[g * cpg + c];
+                b += src[C + g * cpg + c];
+            }
         }
         float* dst = partials + (((long long)s * gridDim.x + blockIdx.x) * G + g) * 2;
         dst[0] = a;
@@ -250,7 +252,7 @@ extern "C" int tc_groupnorm(const void* x, long long ldx, void* y, long long ldy
     if (cap < 1) cap = 1;
     if (cap > kGnMaxPartials) cap = kGnMaxPartials;
     if (nblk > cap) nblk = cap;
-    gn_stats_kernel<<<dim3(nblk, n_stat), threads, 2 * C * sizeof(float), stream>>>(
+    gn_stats_kernel<<<dim3(nblk, n_stat), threads, (size_t)k * 2 * C * sizeof(float), stream>>>(
         reinterpret_cast<const __half*>(x), ldx, pps, C, G, ws);
     count_launch();
     TC_CHECK_LAUNCH("gn_stats_kernel");
