@@ -7,6 +7,8 @@
 //  tc_softmax_rows        row softmax for the unfused d=512 VAE mid-block attention.
 //
 // Reference sites: lvdm/modules/attention.py:81-209,365-412; lvdm/models/autoencoder_dualref.py:172-200,270-341.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 #include "tc_host.h"
 
@@ -261,6 +263,279 @@ __global__ void __launch_bounds__(kAttnThreads, 2) tc_attn_kernel(const __grid_c
     }
 }
 
+// ===================================================================================== fused attention v2
+// Ping-pong over TWO query tiles per CTA with specialised warps:
+//   warps 0-3 / 4-7 : softmax warpgroups for query tile 0 / 1 (one query row per thread)
+//   warp 8          : MMA issuer   (S_w = Q_w K^T, O_w = P_w V; tcgen05, accumulators in TMEM)
+//   warp 9          : TMA producer (Q tiles once, K / V tiles double-buffered)
+// While one warpgroup runs its softmax (MUFU/ALU bound) the tensor core works on the other tile's MMAs.
+constexpr int kAttn2Threads = 320;
+constexpr int kAttn2TmemCols = 512;  // S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
+
+template <bool kTwoSeg>
+__global__ void __launch_bounds__(kAttn2Threads, 1) tc_attn2_kernel(const __grid_constant__ AttnKParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                     // 2 tiles
+    uint8_t* sK = smem + 2 * kTileBytes;    // 2 stages
+    uint8_t* sV = smem + 4 * kTileBytes;    // 2 stages
+    uint8_t* sP = smem + 6 * kTileBytes;    // 2 tiles x 2 sub-tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * kTileBytes);
+    uint64_t* bar_q = bars + 0;
+    uint64_t* k_full = bars + 1;    // [2]
+    uint64_t* k_free = bars + 3;    // [2]
+    uint64_t* v_full = bars + 5;    // [2]
+    uint64_t* v_free = bars + 7;    // [2]
+    uint64_t* s_full = bars + 9;    // [2] per query tile
+    uint64_t* o_full = bars + 11;   // [2]
+    uint64_t* p_ready = bars + 13;  // [2], 128 arrivals
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 15);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int q0 = blockIdx.x * 2 * kQTile;
+    const int head = blockIdx.y;
+    const int qb = blockIdx.z;
+    const int ntiles = (q0 + kQTile < p.Lq) ? 2 : 1;
+
+    if (tid == 0) {
+        tc::mbar_init(bar_q, 1);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&k_full[i], 1);
+            tc::mbar_init(&k_free[i], 1);
+            tc::mbar_init(&v_full[i], 1);
+            tc::mbar_init(&v_free[i], 1);
+            tc::mbar_init(&s_full[i], 1);
+            tc::mbar_init(&o_full[i], 1);
+            tc::mbar_init(&p_ready[i], 128);
+        }
+        tc::fence_mbar_init();
+    }
+    if (warp == 8) {
+        tc::tmem_alloc(tmem_ptr_smem, kAttn2TmemCols);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 9) {
+        // ------------------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            tc::tma_prefetch_desc(&p.tmQ);
+            tc::mbar_arrive_expect_tx(bar_q, (uint32_t)(ntiles * kTileBytes));
+            for (int w = 0; w < ntiles; ++w) tc::tma_load_3d(sQ + w * kTileBytes, &p.tmQ, bar_q, head * 64, q0 + w * kQTile, qb);
+            int g = 0;
+            for (int seg = 0; seg < p.n_seg; ++seg) {
+                const int nblk = (p.Lk[seg] + kKVTile - 1) / kKVTile;
+                const int kvb = qb / p.kv_div[seg];
+                for (int j = 0; j < nblk; ++j, ++g) {
+                    const int st = g & 1;
+                    const uint32_t ph = (uint32_t)((g >> 1) & 1);
+                    tc::mbar_wait(&k_free[st], ph ^ 1u);
+                    tc::mbar_arrive_expect_tx(&k_full[st], kTileBytes);
+                    tc::tma_load_3d(sK + st * kTileBytes, &p.tmK[seg], &k_full[st], head * 64, j * kKVTile, kvb);
+                    tc::mbar_wait(&v_free[st], ph ^ 1u);
+                    tc::mbar_arrive_expect_tx(&v_full[st], kTileBytes);
+                    tc::tma_load_3d(sV + st * kTileBytes, &p.tmV[seg], &v_full[st], head * 64, j * kKVTile, kvb);
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // ------------------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t sQ_a = tc::smem_u32(sQ), sK_a = tc::smem_u32(sK), sV_a = tc::smem_u32(sV), sP_a = tc::smem_u32(sP);
+            int G = 0;
+            for (int seg = 0; seg < p.n_seg; ++seg) G += (p.Lk[seg] + kKVTile - 1) / kKVTile;
+            // per-block key counts, walked in lock-step with the other roles
+            auto block_nk = [&](int gi) {
+                int seg = 0, j = gi;
+                while (true) {
+                    const int nb = (p.Lk[seg] + kKVTile - 1) / kKVTile;
+                    if (j < nb) break;
+                    j -= nb;
+                    ++seg;
+                }
+                const int left = p.Lk[seg] - j * kKVTile;
+                return left < kKVTile ? ((left + 15) & ~15) : kKVTile;
+            };
+            auto issue_s = [&](int w, int st, int nk) {
+                const uint32_t idesc = tc::umma_idesc_f16(128, (uint32_t)nk, 0, 0);
+                const uint64_t qd = tc::umma_desc_sw128(sQ_a + (uint32_t)w * kTileBytes);
+                const uint64_t kd = tc::umma_desc_sw128(sK_a + (uint32_t)st * kTileBytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc::umma_f16(tmem_base + (uint32_t)w * 128, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc, k != 0);
+            };
+            tc::mbar_wait(bar_q, 0);
+            tc::mbar_wait(&k_full[0], 0);
+            tc::tc_fence_after();
+            {
+                const int nk = block_nk(0);
+                for (int w = 0; w < ntiles; ++w) {
+                    issue_s(w, 0, nk);
+                    tc::umma_commit(&s_full[w]);
+                }
+                tc::umma_commit(&k_free[0]);
+            }
+            for (int g = 0; g < G; ++g) {
+                const int st = g & 1;
+                const int nk = block_nk(g);
+                const int nk_next = (g + 1 < G) ? block_nk(g + 1) : 0;
+                for (int w = 0; w < ntiles; ++w) {
+                    tc::mbar_wait(&p_ready[w], (uint32_t)(g & 1));
+                    if (w == 0) tc::mbar_wait(&v_full[st], (uint32_t)((g >> 1) & 1));
+                    tc::tc_fence_after();
+                    const uint32_t idesc_o = tc::umma_idesc_f16(128, 64, 0, 1);  // B (= V tile) MN-major
+                    const uint64_t vd = tc::umma_desc_sw128(sV_a + (uint32_t)st * kTileBytes);
+                    for (int t = 0; t < nk / 16; ++t) {
+                        const uint64_t pd = tc::umma_desc_sw128(sP_a + (uint32_t)(2 * w + (t >> 2)) * kTileBytes) + (uint64_t)((t & 3) * 2);
+                        tc::umma_f16(tmem_base + 256 + (uint32_t)w * 64, pd, vd + (uint64_t)(t * 128), idesc_o, t != 0);
+                    }
+                    tc::umma_commit(&o_full[w]);
+                    if (w == ntiles - 1) tc::umma_commit(&v_free[st]);
+                    if (g + 1 < G) {
+                        const int st1 = (g + 1) & 1;
+                        if (w == 0) {
+                            tc::mbar_wait(&k_full[st1], (uint32_t)(((g + 1) >> 1) & 1));
+                            tc::tc_fence_after();
+                        }
+                        issue_s(w, st1, nk_next);
+                        tc::umma_commit(&s_full[w]);
+                        if (w == ntiles - 1) tc::umma_commit(&k_free[st1]);
+                    }
+                }
+            }
+        }
+    } else if ((warp >> 2) < ntiles) {
+        // ------------------------------------------------------------------------------ softmax warpgroups
+        const int w = warp >> 2;
+        const int row = tid & 127;
+        const uint32_t lane_off = ((uint32_t)((warp & 3) * 32)) << 16;
+        const uint32_t tmem_s = tmem_base + (uint32_t)w * 128 + lane_off;
+        const uint32_t tmem_o = tmem_base + 256 + (uint32_t)w * 64 + lane_off;
+        uint8_t* sPw = sP + (size_t)(2 * w) * kTileBytes;
+        float o_total[kTwoSeg ? 64 : 1];   // sum over segments (text + image cross attention) only when needed
+        if constexpr (kTwoSeg) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) o_total[i] = 0.f;
+        }
+        float o_acc[64];
+        int g = 0;
+        for (int seg = 0; seg < p.n_seg; ++seg) {
+            const int Lk = p.Lk[seg];
+            const int nblk = (Lk + kKVTile - 1) / kKVTile;
+            float m_run = -INFINITY, l_run = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+            for (int j = 0; j < nblk; ++j, ++g) {
+                const int kv_left = Lk - j * kKVTile;
+                const int nvalid = kv_left < kKVTile ? kv_left : kKVTile;
+                const int nk = (nvalid + 15) & ~15;
+                tc::mbar_wait(&s_full[w], (uint32_t)(g & 1));
+                tc::tc_fence_after();
+                float m_blk = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c * 16 < nk) {
+                        uint32_t r[16];
+                        tc::tmem_ld16(tmem_s + (uint32_t)(c * 16), r);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c * 16 + i < nvalid) m_blk = fmaxf(m_blk, __uint_as_float(r[i]));
+                    }
+                }
+                const float m_new = fmaxf(m_run, m_blk);
+                const float m_scaled = m_new * p.scale_log2;
+                const float alpha = fast_exp2(m_run * p.scale_log2 - m_scaled);
+                float l_blk = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c * 16 < nk) {
+                        uint32_t r[16];
+                        tc::tmem_ld16(tmem_s + (uint32_t)(c * 16), r);
+                        tc::tmem_ld_wait();
+                        float pv[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float e = fast_exp2(__uint_as_float(r[i]) * p.scale_log2 - m_scaled);
+                            pv[i] = (c * 16 + i < nvalid) ? e : 0.f;
+                            l_blk += pv[i];
+                        }
+                        uint4 u0, u1;
+                        __half2 h[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(pv[2 * i], pv[2 * i + 1]);
+                        u0.x = *reinterpret_cast<uint32_t*>(&h[0]);
+                        u0.y = *reinterpret_cast<uint32_t*>(&h[1]);
+                        u0.z = *reinterpret_cast<uint32_t*>(&h[2]);
+                        u0.w = *reinterpret_cast<uint32_t*>(&h[3]);
+                        u1.x = *reinterpret_cast<uint32_t*>(&h[4]);
+                        u1.y = *reinterpret_cast<uint32_t*>(&h[5]);
+                        u1.z = *reinterpret_cast<uint32_t*>(&h[6]);
+                        u1.w = *reinterpret_cast<uint32_t*>(&h[7]);
+                        uint8_t* sub = sPw + (c >> 2) * kTileBytes + row * 128;
+                        const int ch0 = (c & 3) * 2;
+                        *reinterpret_cast<uint4*>(sub + (((ch0) ^ (row & 7)) << 4)) = u0;
+                        *reinterpret_cast<uint4*>(sub + (((ch0 + 1) ^ (row & 7)) << 4)) = u1;
+                    }
+                }
+                l_run = l_run * alpha + l_blk;
+                m_run = m_new;
+                tc::fence_proxy_async_smem();
+                tc::tc_fence_before();
+                tc::mbar_arrive(&p_ready[w]);
+                // O_blk of this block: o_acc = o_acc * alpha + P V
+                tc::mbar_wait(&o_full[w], (uint32_t)(g & 1));
+                tc::tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[16];
+                    tc::tmem_ld16(tmem_o + (uint32_t)(c * 16), r);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] = fmaf(o_acc[c * 16 + i], alpha, __uint_as_float(r[i]));
+                }
+            }
+            const float inv_l = 1.0f / l_run;
+            if constexpr (kTwoSeg) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) o_total[i] += o_acc[i] * inv_l;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) o_acc[i] *= inv_l;
+            }
+        }
+        const float* o_fin = kTwoSeg ? o_total : o_acc;
+        const int qrow = q0 + w * kQTile + row;
+        if (qrow < p.Lq) {
+            __half* dst = p.out + ((long long)qb * p.Lq + qrow) * p.ldo + head * 64;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                __half2 h[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(o_fin[c * 8 + 2 * i], o_fin[c * 8 + 2 * i + 1]);
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h[0]);
+                u.y = *reinterpret_cast<uint32_t*>(&h[1]);
+                u.z = *reinterpret_cast<uint32_t*>(&h[2]);
+                u.w = *reinterpret_cast<uint32_t*>(&h[3]);
+                reinterpret_cast<uint4*>(dst)[c] = u;
+            }
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, kAttn2TmemCols);
+    }
+}
+
 // ===================================================================================== temporal attention
 // x[b][t][p][heads*64]; one (b, p, head) item per group of kGroup lanes (lane i of the group = query frame i).
 template <int kGroup>
@@ -436,19 +711,43 @@ extern "C" int tc_attention(const TcAttention* d, void* stream_v) {
     p.out = reinterpret_cast<__half*>(d->out);
     p.ldo = d->ldo;
     p.scale_log2 = d->scale * 1.4426950408889634f;
-    const size_t smem_bytes = 5 * kTileBytes + 1024 + 128;
-    static bool attr_set = false;
-    if (!attr_set) {
-        int rc = check_cuda(
-            cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
-            "cudaFuncSetAttribute(tc_attn_kernel)");
-        if (rc) return rc;
-        attr_set = true;
+    static const bool use_v1 = (getenv("TC_ATTN_V1") != nullptr);   // A/B switch during bring-up
+    if (use_v1) {
+        const size_t smem_bytes = 5 * kTileBytes + 1024 + 128;
+        static bool attr_set = false;
+        if (!attr_set) {
+            int rc = check_cuda(
+                cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
+                "cudaFuncSetAttribute(tc_attn_kernel)");
+            if (rc) return rc;
+            attr_set = true;
+        }
+        dim3 grid((d->Lq + kQTile - 1) / kQTile, d->heads, d->q_batches);
+        tc_attn_kernel<<<grid, kAttnThreads, smem_bytes, stream>>>(p);
+        count_launch();
+        TC_CHECK_LAUNCH("tc_attn_kernel");
+        return TC_OK;
     }
-    dim3 grid((d->Lq + kQTile - 1) / kQTile, d->heads, d->q_batches);
-    tc_attn_kernel<<<grid, kAttnThreads, smem_bytes, stream>>>(p);
+    const size_t smem_bytes = 10 * kTileBytes + 1024 + 256;
+    static bool attr2_set = false;
+    if (!attr2_set) {
+        int rc = check_cuda(cudaFuncSetAttribute(tc_attn2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem_bytes),
+                            "cudaFuncSetAttribute(tc_attn2_kernel<false>)");
+        if (rc) return rc;
+        rc = check_cuda(cudaFuncSetAttribute(tc_attn2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem_bytes),
+                        "cudaFuncSetAttribute(tc_attn2_kernel<true>)");
+        if (rc) return rc;
+        attr2_set = true;
+    }
+    dim3 grid((d->Lq + 2 * kQTile - 1) / (2 * kQTile), d->heads, d->q_batches);
+    if (d->n_seg == 2)
+        tc_attn2_kernel<true><<<grid, kAttn2Threads, smem_bytes, stream>>>(p);
+    else
+        tc_attn2_kernel<false><<<grid, kAttn2Threads, smem_bytes, stream>>>(p);
     count_launch();
-    TC_CHECK_LAUNCH("tc_attn_kernel");
+    TC_CHECK_LAUNCH("tc_attn2_kernel");
     return TC_OK;
 }
 
