@@ -110,13 +110,9 @@ def build_model(dev, rank, world):
             for k, prm in m.named_parameters():
                 prm.copy_(synthetic.synthetic_tensor(k, tuple(prm.shape), 0).to(dev))
         if world > 1:
-            import torch.distributed as dist
+            from tooncrafter_b200.distributed import broadcast_parameters
             # ONE broadcast of the weights at init; no collective on the data path afterwards
-            flat = torch._utils._flatten_dense_tensors([prm.data for prm in m.parameters()])
-            dist.broadcast(flat, src=0)
-            for prm, src in zip(m.parameters(), torch._utils._unflatten_dense_tensors(flat, [prm.data for prm in m.parameters()])):
-                prm.data.copy_(src)
-            del flat
+            broadcast_parameters(m, src=0)
     m.perframe_ae = True
     return m.eval()
 
@@ -269,7 +265,9 @@ def main():
     model = build_model(dev, rank, world)
     sampler = DDIMSampler(model)
     fs = torch.tensor([10], device=dev)
-    hi = host_inputs(seed=123 + rank)                      # per-rank clip (seed + global clip index)
+    from tooncrafter_b200.distributed import clip_seed, shard_clips
+    my_clip = shard_clips(world, rank, world)[0]           # one clip per GPU per step (weak scaling)
+    hi = host_inputs(seed=clip_seed(123, my_clip))          # per-clip seed: results independent of the world size
     di = to_device(hi, dev)
     torch.cuda.synchronize()
 
