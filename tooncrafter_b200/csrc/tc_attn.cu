@@ -3,7 +3,7 @@
 //  tc_attention           fused softmax(QK^T)V, head dim 64, tcgen05 MMAs (S = QK^T and O = PV) with TMEM
 //                         accumulators, TMA-staged Q/K/V tiles, fp32 online softmax, one query row per thread.
 //                         Two CTAs per SM: one CTA's softmax overlaps the other's MMAs.
-//  tc_temporal_attention  16-frame temporal self-attention, one (pixel, head) per half-warp (memory-bound).
+//  tc_temporal_attention  16-frame temporal self-attention, one (pixel, head) per warp, mma.sync 16x8x16 (HBM-bound).
 //  tc_softmax_rows        row softmax for the unfused d=512 VAE mid-block attention.
 //
 // Reference sites: lvdm/modules/attention.py:81-209,365-412; lvdm/models/autoencoder_dualref.py:172-200,270-341.
@@ -37,6 +37,10 @@ __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+__device__ __forceinline__ uint32_t pack_h2(float x, float y) {
+    __half2 h = __floats2half2_rn(x, y);
+    return *reinterpret_cast<uint32_t*>(&h);
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 2) tc_attn_kernel(const __grid_constant__ AttnKParams p) {
@@ -436,51 +440,97 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) tc_attn2_kernel(const __grid
                 const int nk = (nvalid + 15) & ~15;
                 tc::mbar_wait(&s_full[w], (uint32_t)(g & 1));
                 tc::tc_fence_after();
-                float m_blk = -INFINITY;
+                // ---- pass 1: row max.  Full blocks take the unpredicated path with 4 independent max chains
+                // (the serial FMNMX / FADD chains were the softmax warps' critical path: 2 warps per scheduler).
+                float m_blk;
+                const bool full = (nvalid == kKVTile);
+                if (full) {
+                    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    if (c * 16 < nk) {
-                        uint32_t r[16];
-                        tc::tmem_ld16(tmem_s + (uint32_t)(c * 16), r);
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t r[32];
+                        tc::tmem_ld32(tmem_s + (uint32_t)(c * 32), r);
                         tc::tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (c * 16 + i < nvalid) m_blk = fmaxf(m_blk, __uint_as_float(r[i]));
+                        for (int i = 0; i < 32; i += 4) {
+                            mx[0] = fmaxf(mx[0], __uint_as_float(r[i]));
+                            mx[1] = fmaxf(mx[1], __uint_as_float(r[i + 1]));
+                            mx[2] = fmaxf(mx[2], __uint_as_float(r[i + 2]));
+                            mx[3] = fmaxf(mx[3], __uint_as_float(r[i + 3]));
+                        }
+                    }
+                    m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+                } else {
+                    m_blk = -INFINITY;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        if (c * 16 < nk) {
+                            uint32_t r[16];
+                            tc::tmem_ld16(tmem_s + (uint32_t)(c * 16), r);
+                            tc::tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (c * 16 + i < nvalid) m_blk = fmaxf(m_blk, __uint_as_float(r[i]));
+                        }
                     }
                 }
                 const float m_new = fmaxf(m_run, m_blk);
                 const float m_scaled = m_new * p.scale_log2;
                 const float alpha = fast_exp2(m_run * p.scale_log2 - m_scaled);
-                float l_blk = 0.f;
+                // ---- pass 2: p = exp2(s * scale - m * scale), row sum, P tile (fp16, K-major, 128B swizzle) to smem
+                float l_blk;
+                if (full) {
+                    float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    if (c * 16 < nk) {
-                        uint32_t r[16];
-                        tc::tmem_ld16(tmem_s + (uint32_t)(c * 16), r);
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t r[32];
+                        tc::tmem_ld32(tmem_s + (uint32_t)(c * 32), r);
                         tc::tmem_ld_wait();
-                        float pv[16];
+                        uint32_t pk[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float e = fast_exp2(__uint_as_float(r[i]) * p.scale_log2 - m_scaled);
-                            pv[i] = (c * 16 + i < nvalid) ? e : 0.f;
-                            l_blk += pv[i];
+                        for (int i = 0; i < 32; i += 4) {
+                            const float e0 = fast_exp2(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_scaled));
+                            const float e1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -m_scaled));
+                            const float e2 = fast_exp2(fmaf(__uint_as_float(r[i + 2]), p.scale_log2, -m_scaled));
+                            const float e3 = fast_exp2(fmaf(__uint_as_float(r[i + 3]), p.scale_log2, -m_scaled));
+                            ls[0] += e0;
+                            ls[1] += e1;
+                            ls[2] += e2;
+                            ls[3] += e3;
+                            pk[i / 2] = pack_h2(e0, e1);
+                            pk[i / 2 + 1] = pack_h2(e2, e3);
                         }
-                        uint4 u0, u1;
-                        __half2 h[8];
+                        uint8_t* sub = sPw + (c >> 1) * kTileBytes + row * 128;
+                        const int ch0 = (c & 1) * 4;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(pv[2 * i], pv[2 * i + 1]);
-                        u0.x = *reinterpret_cast<uint32_t*>(&h[0]);
-                        u0.y = *reinterpret_cast<uint32_t*>(&h[1]);
-                        u0.z = *reinterpret_cast<uint32_t*>(&h[2]);
-                        u0.w = *reinterpret_cast<uint32_t*>(&h[3]);
-                        u1.x = *reinterpret_cast<uint32_t*>(&h[4]);
-                        u1.y = *reinterpret_cast<uint32_t*>(&h[5]);
-                        u1.z = *reinterpret_cast<uint32_t*>(&h[6]);
-                        u1.w = *reinterpret_cast<uint32_t*>(&h[7]);
-                        uint8_t* sub = sPw + (c >> 2) * kTileBytes + row * 128;
-                        const int ch0 = (c & 3) * 2;
-                        *reinterpret_cast<uint4*>(sub + (((ch0) ^ (row & 7)) << 4)) = u0;
-                        *reinterpret_cast<uint4*>(sub + (((ch0 + 1) ^ (row & 7)) << 4)) = u1;
+                        for (int q4 = 0; q4 < 4; ++q4)
+                            *reinterpret_cast<uint4*>(sub + (((ch0 + q4) ^ (row & 7)) << 4)) =
+                                make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+                    }
+                    l_blk = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+                } else {
+                    l_blk = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        if (c * 16 < nk) {
+                            uint32_t r[16];
+                            tc::tmem_ld16(tmem_s + (uint32_t)(c * 16), r);
+                            tc::tmem_ld_wait();
+                            uint32_t pk[8];
+#pragma unroll
+                            for (int i = 0; i < 16; i += 2) {
+                                float e0 = fast_exp2(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_scaled));
+                                float e1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -m_scaled));
+                                e0 = (c * 16 + i < nvalid) ? e0 : 0.f;
+                                e1 = (c * 16 + i + 1 < nvalid) ? e1 : 0.f;
+                                l_blk += e0 + e1;
+                                pk[i / 2] = pack_h2(e0, e1);
+                            }
+                            uint8_t* sub = sPw + (c >> 2) * kTileBytes + row * 128;
+                            const int ch0 = (c & 3) * 2;
+                            *reinterpret_cast<uint4*>(sub + (((ch0) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            *reinterpret_cast<uint4*>(sub + (((ch0 + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        }
                     }
                 }
                 l_run = l_run * alpha + l_blk;
@@ -492,12 +542,12 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) tc_attn2_kernel(const __grid
                 tc::mbar_wait(&o_full[w], (uint32_t)(g & 1));
                 tc::tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t r[16];
-                    tc::tmem_ld16(tmem_o + (uint32_t)(c * 16), r);
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t r[32];
+                    tc::tmem_ld32(tmem_o + (uint32_t)(c * 32), r);
                     tc::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] = fmaf(o_acc[c * 16 + i], alpha, __uint_as_float(r[i]));
+                    for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha, __uint_as_float(r[i]));
                 }
             }
             const float inv_l = 1.0f / l_run;
@@ -641,6 +691,136 @@ __global__ void temporal_attn_kernel(const __half* __restrict__ q, const __half*
     }
 }
 
+// ===================================================================================== temporal attention, T <= 16
+// One warp per (batch, pixel, head): the whole problem is a 16 x 16 x 64 attention, far below the 128-row tcgen05 tile,
+// and the kernel is HBM-bound (reads q, k, v once, writes o once).  S = Q K^T and O = P V use warp-level
+// mma.sync.m16n8k16 with fragments loaded straight from global memory (Q, K) or via ldmatrix.trans from a
+// swizzled 2 KiB smem tile (V); softmax in fp32 on the accumulator fragments.
+__device__ __forceinline__ void mma_m16n8k16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(128) temporal_attn_mma_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
+                                                                const __half* __restrict__ v, long long ld,
+                                                                __half* __restrict__ out, long long ldo, int B, int T,
+                                                                int P, int heads, float scale_log2) {
+    __shared__ __align__(128) uint8_t sV[4][16 * 128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const long long total = (long long)B * P * heads;
+    const long long frame_stride = (long long)P * ld;       // elements between consecutive frames of one pixel
+    uint8_t* sv = sV[warp];
+    for (long long item = (long long)blockIdx.x * 4 + warp; item < total; item += (long long)gridDim.x * 4) {
+        const int h = (int)(item % heads);
+        const long long r = item / heads;
+        const long long pix = r % P, b = r / P;
+        const long long base = ((b * T) * P + pix) * ld + h * 64;   // frame 0 of this (b, pix, head)
+        // ---- V tile -> smem (16-byte chunks, XOR-swizzled so ldmatrix rows hit distinct banks)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int chunk = lane + 32 * i;
+            const int row = chunk >> 3, c16 = chunk & 7;
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            if (row < T) u = *reinterpret_cast<const uint4*>(v + base + row * frame_stride + c16 * 8);
+            *reinterpret_cast<uint4*>(sv + row * 128 + ((c16 ^ (row & 7)) << 4)) = u;
+        }
+        // ---- Q (A fragments) and K (B fragments) straight from global
+        uint32_t qa[4][4], kb[2][4][2];
+        const bool r0 = g < T, r1 = g + 8 < T;
+        const __half* q0p = q + base + (long long)g * frame_stride;
+        const __half* q1p = q + base + (long long)(g + 8) * frame_stride;
+        const __half* k0p = k + base + (long long)g * frame_stride;
+        const __half* k1p = k + base + (long long)(g + 8) * frame_stride;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const int c = 16 * ks + 2 * t4;
+            qa[ks][0] = r0 ? *reinterpret_cast<const uint32_t*>(q0p + c) : 0u;
+            qa[ks][1] = r1 ? *reinterpret_cast<const uint32_t*>(q1p + c) : 0u;
+            qa[ks][2] = r0 ? *reinterpret_cast<const uint32_t*>(q0p + c + 8) : 0u;
+            qa[ks][3] = r1 ? *reinterpret_cast<const uint32_t*>(q1p + c + 8) : 0u;
+            kb[0][ks][0] = r0 ? *reinterpret_cast<const uint32_t*>(k0p + c) : 0u;
+            kb[0][ks][1] = r0 ? *reinterpret_cast<const uint32_t*>(k0p + c + 8) : 0u;
+            kb[1][ks][0] = r1 ? *reinterpret_cast<const uint32_t*>(k1p + c) : 0u;
+            kb[1][ks][1] = r1 ? *reinterpret_cast<const uint32_t*>(k1p + c + 8) : 0u;
+        }
+        float sacc[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sacc[nt][i] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) mma_m16n8k16(sacc[nt], qa[ks], kb[nt][ks][0], kb[nt][ks][1]);
+        }
+        // ---- softmax over the 16 keys of rows g and g + 8 (a row lives in the 4 lanes of a quad)
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const bool key_ok = (8 * nt + 2 * t4 + i) < T;
+                sacc[nt][i] = key_ok ? sacc[nt][i] * scale_log2 : -INFINITY;
+                sacc[nt][2 + i] = key_ok ? sacc[nt][2 + i] * scale_log2 : -INFINITY;
+                m0 = fmaxf(m0, sacc[nt][i]);
+                m1 = fmaxf(m1, sacc[nt][2 + i]);
+            }
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                sacc[nt][i] = exp2f(sacc[nt][i] - m0);
+                sacc[nt][2 + i] = exp2f(sacc[nt][2 + i] - m1);
+                l0 += sacc[nt][i];
+                l1 += sacc[nt][2 + i];
+            }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+        uint32_t pa[4];
+        pa[0] = pack_h2(sacc[0][0] * inv0, sacc[0][1] * inv0);
+        pa[1] = pack_h2(sacc[0][2] * inv1, sacc[0][3] * inv1);
+        pa[2] = pack_h2(sacc[1][0] * inv0, sacc[1][1] * inv0);
+        pa[3] = pack_h2(sacc[1][2] * inv1, sacc[1][3] * inv1);
+        __syncwarp();
+        // ---- O = P V, V fragments by ldmatrix.trans (two 8-wide d tiles per instruction)
+        __half* o0p = out + ((b * T + g) * P + pix) * ldo + h * 64;
+        __half* o1p = out + ((b * T + g + 8) * P + pix) * ldo + h * 64;
+#pragma unroll
+        for (int nd = 0; nd < 8; nd += 2) {
+            // lane i supplies the row address of matrix i/8: matrices (k 0-7, nd), (k 8-15, nd), (k 0-7, nd+1), (k 8-15, nd+1)
+            const int mrow = (lane & 7) + ((lane >> 3) & 1) * 8;
+            const int mcol = nd + (lane >> 4);
+            const uint32_t addr = tc::smem_u32(sv + mrow * 128 + ((mcol ^ (mrow & 7)) << 4));
+            uint32_t b0, b1, b2, b3;
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                         : "r"(addr));
+            float oa[4] = {0.f, 0.f, 0.f, 0.f}, ob[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_m16n8k16(oa, pa, b0, b1);
+            mma_m16n8k16(ob, pa, b2, b3);
+            if (r0) {
+                *reinterpret_cast<uint32_t*>(o0p + 8 * nd + 2 * t4) = pack_h2(oa[0], oa[1]);
+                *reinterpret_cast<uint32_t*>(o0p + 8 * (nd + 1) + 2 * t4) = pack_h2(ob[0], ob[1]);
+            }
+            if (r1) {
+                *reinterpret_cast<uint32_t*>(o1p + 8 * nd + 2 * t4) = pack_h2(oa[2], oa[3]);
+                *reinterpret_cast<uint32_t*>(o1p + 8 * (nd + 1) + 2 * t4) = pack_h2(ob[2], ob[3]);
+            }
+        }
+        __syncwarp();   // smem V tile is reused by the next item
+    }
+}
+
 // ===================================================================================== row softmax (in place)
 __global__ void softmax_rows_kernel(__half* __restrict__ s, long long lds, int rows, int cols, float scale_log2) {
     const int row = blockIdx.x;
@@ -764,8 +944,10 @@ extern "C" int tc_temporal_attention(const void* q, const void* k, const void* v
     const __half* vp = reinterpret_cast<const __half*>(v);
     __half* op = reinterpret_cast<__half*>(out);
     if (T <= 16) {
-        const long long blocks = (items + 7) / 8;
-        temporal_attn_kernel<16><<<(unsigned)blocks, 128, 0, stream>>>(qp, kp, vp, ld, op, ldo, B, T, P, heads, sl2);
+        long long blocks = (items + 3) / 4;
+        const long long cap = 16LL * sm_count();
+        if (blocks > cap) blocks = cap;
+        temporal_attn_mma_kernel<<<(unsigned)blocks, 128, 0, stream>>>(qp, kp, vp, ld, op, ldo, B, T, P, heads, sl2);
     } else {
         const long long blocks = (items + 3) / 4;
         temporal_attn_kernel<32><<<(unsigned)blocks, 128, 0, stream>>>(qp, kp, vp, ld, op, ldo, B, T, P, heads, sl2);
