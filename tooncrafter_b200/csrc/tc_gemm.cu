@@ -12,6 +12,8 @@
 //                                *scale, +residual, optional GEGLU -> fp16 -> 16-byte global stores
 //
 // Roofline: tensor-bound (fp16 dense); algorithmic flops = 2 * M * n_cols * taps * C.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 #include "tc_host.h"
 
@@ -73,6 +75,10 @@ __device__ __forceinline__ void store_row16(__half* dst, const float (&v)[16], i
     }
 }
 
+// kPair = true: two CTAs of a cluster form one tcgen05 cta_group::2 pair (M = 256 per MMA, each CTA loads its own 128
+// A rows and HALF of the B tile), which cuts the shared-memory/L2 operand traffic per MAC by ~30-45 % — the single-CTA
+// kernel saturates at ~62 B/clk/SM of TMA ingest (profiles/r01_*conv320*).
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ GemmKParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -81,7 +87,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     const int lane = threadIdx.x & 31;
     const int S = p.stages;
     const int BN = p.BN;
-    const uint32_t b_stage_bytes = (uint32_t)BN * 128u;
+    const uint32_t rank = kPair ? tc::cluster_ctarank() : 0u;      // 0 = leader (issues the MMAs)
+    const int b_rows = kPair ? (BN >> 1) : BN;                      // B rows staged by THIS CTA
+    const uint32_t b_stage_bytes = (uint32_t)b_rows * 128u;
 
     uint8_t* sA = smem;
     uint8_t* sB = smem + (size_t)S * kAStageBytes;
@@ -102,43 +110,64 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         }
         for (int a = 0; a < 2; ++a) {
             tc::mbar_init(&tfull_bar[a], 1);
-            tc::mbar_init(&tempty_bar[a], 8);
+            tc::mbar_init(&tempty_bar[a], kPair ? 16 : 8);   // epilogue warps of both CTAs release the leader
         }
         tc::fence_mbar_init();
     }
     if (warp == 2) {
-        tc::tmem_alloc(tmem_ptr_smem, kTmemCols);
-        tc::tmem_relinquish();
+        if constexpr (kPair) {
+            tc::tmem_alloc_pair(tmem_ptr_smem, kTmemCols);
+            tc::tmem_relinquish_pair();
+        } else {
+            tc::tmem_alloc(tmem_ptr_smem, kTmemCols);
+            tc::tmem_relinquish();
+        }
     }
     tc::tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) tc::cluster_sync_all(); else __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int total_tiles = p.tiles_m * p.tiles_nn;
+    // work units: a single CTA takes one M tile, a CTA pair takes two consecutive M tiles (rank selects which)
+    const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_units = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int tiles_mu = kPair ? ((p.tiles_m + 1) >> 1) : p.tiles_m;
+    const int total_tiles = tiles_mu * p.tiles_nn;
     const int kblocks = p.taps * p.kc_per_tap;
+    // tile -> (nt, mt) for this CTA; mt >= tiles_m (odd tail of a pair) decodes to out-of-range coordinates:
+    // its TMA boxes are zero-filled and its rows are never stored
+#define TC_DECODE_TILE(tile)                                                   \
+    const int nt = (tile) / tiles_mu;                                          \
+    const int mt = ((tile) - nt * tiles_mu) * (kPair ? 2 : 1) + (int)rank;     \
+    const int tx = mt % p.tiles_x;                                             \
+    const int ty = (mt / p.tiles_x) % p.tiles_y;                               \
+    const int tn = mt / (p.tiles_x * p.tiles_y);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile / p.tiles_m;
-                const int mt = tile - nt * p.tiles_m;
-                const int tx = mt % p.tiles_x;
-                const int ty = (mt / p.tiles_x) % p.tiles_y;
-                const int tn = mt / (p.tiles_x * p.tiles_y);
+            for (int tile = unit; tile < total_tiles; tile += n_units) {
+                TC_DECODE_TILE(tile)
                 const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
                 for (int tap = 0; tap < p.taps; ++tap) {
                     const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap], an = n0 + p.tap_dn[tap];
                     for (int kc = 0; kc < p.kc_per_tap; ++kc) {
                         tc::mbar_wait(&empty_bar[stage], phase ^ 1u);
-                        tc::mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + b_stage_bytes);
-                        tc::tma_load_4d(sA + (size_t)stage * kAStageBytes, &p.tmA, &full_bar[stage], kc * kBlockK, ax,
-                                        ay, an);
-                        tc::tma_load_2d(sB + (size_t)stage * b_stage_bytes, &p.tmB, &full_bar[stage],
-                                        (tap * p.kc_per_tap + kc) * kBlockK, nt * BN);
+                        uint8_t* dA = sA + (size_t)stage * kAStageBytes;
+                        uint8_t* dB = sB + (size_t)stage * b_stage_bytes;
+                        const int kcol = (tap * p.kc_per_tap + kc) * kBlockK;
+                        if constexpr (kPair) {
+                            // both CTAs' bytes are credited to the leader's barrier
+                            if (rank == 0) tc::mbar_arrive_expect_tx(&full_bar[stage], 2u * (p.a_bytes + b_stage_bytes));
+                            tc::tma_load_4d_pair(dA, &p.tmA, &full_bar[stage], kc * kBlockK, ax, ay, an);
+                            tc::tma_load_2d_pair(dB, &p.tmB, &full_bar[stage], kcol, nt * BN + (int)rank * b_rows);
+                        } else {
+                            tc::mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + b_stage_bytes);
+                            tc::tma_load_4d(dA, &p.tmA, &full_bar[stage], kc * kBlockK, ax, ay, an);
+                            tc::tma_load_2d(dB, &p.tmB, &full_bar[stage], kcol, nt * BN);
+                        }
                         if (++stage == S) {
                             stage = 0;
                             phase ^= 1u;
@@ -149,14 +178,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = tc::umma_idesc_f16(kBlockM, (uint32_t)BN, 0, 0);
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = tc::umma_idesc_f16(kPair ? 2 * kBlockM : kBlockM, (uint32_t)BN, 0, 0);
             const uint32_t sA_addr = tc::smem_u32(sA), sB_addr = tc::smem_u32(sB);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = unit; tile < total_tiles; tile += n_units) {
                 tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
                 tc::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
@@ -168,16 +197,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // advance 16 halfs = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
-                        tc::umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                                     (kb | k) != 0 ? 1u : 0u);
+                        if constexpr (kPair)
+                            tc::umma_f16_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                              (kb | k) != 0 ? 1u : 0u);
+                        else
+                            tc::umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                         (kb | k) != 0 ? 1u : 0u);
                     }
-                    tc::umma_commit(&empty_bar[stage]);
+                    if constexpr (kPair) tc::umma_commit_pair(&empty_bar[stage]); else tc::umma_commit(&empty_bar[stage]);
                     if (++stage == S) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                tc::umma_commit(&tfull_bar[acc]);
+                if constexpr (kPair) tc::umma_commit_pair(&tfull_bar[acc]); else tc::umma_commit(&tfull_bar[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
@@ -202,12 +235,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         const bool vec_ok = (p.n_cols % 16) == 0;                   // all chunks complete -> 16-byte paths
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int nt = tile / p.tiles_m;
-            const int mt = tile - nt * p.tiles_m;
-            const int tx = mt % p.tiles_x;
-            const int ty = (mt / p.tiles_x) % p.tiles_y;
-            const int tn = mt / (p.tiles_x * p.tiles_y);
+        for (int tile = unit; tile < total_tiles; tile += n_units) {
+            TC_DECODE_TILE(tile)
             const int x = tx * p.TW + rx, y = ty * p.TH + ry, n = tn * p.TN + rn;
             const bool row_ok = (rn < p.TN) && (x < p.oW) && (y < p.oH) && (n < p.oN);
             const long long m = ((long long)n * p.oH + y) * p.oW + x;
@@ -334,17 +363,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             }
             tc::tc_fence_before();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if constexpr (kPair) tc::mbar_arrive_cluster(&tempty_bar[acc], 0); else tc::mbar_arrive(&tempty_bar[acc]);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
     }
+#undef TC_DECODE_TILE
 
     tc::tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) tc::cluster_sync_all(); else __syncthreads();   // the peer may still read our smem / barriers
     if (warp == 2) {
         tc::tc_fence_after();
-        tc::tmem_dealloc(tmem_base, kTmemCols);
+        if constexpr (kPair) tc::tmem_dealloc_pair(tmem_base, kTmemCols); else tc::tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -447,16 +479,21 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
         if (!m) return TC_ERR_CUDA;
         p.tmA = *m;
     }
+    // CTA-pair mode when there is enough work to give every SM pair at least one tile pair
+    static const char* pair_env = getenv("TC_GEMM_PAIR");       // "0" / "1" force (A/B testing), unset = heuristic
+    const long long pair_tiles = (long long)((p.tiles_m + 1) / 2) * p.tiles_nn;
+    bool pair = p.tiles_m >= 2 && pair_tiles >= sm_count() / 2;
+    if (pair_env) pair = (pair_env[0] == '1') && p.tiles_m >= 2;
     {
         uint64_t dims[2] = {(uint64_t)d->taps * (uint64_t)d->a_C, (uint64_t)d->b_rows};
         uint64_t strides[1] = {(uint64_t)d->ldb * 2};
-        uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)BN};
+        uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)(pair ? BN / 2 : BN)};
         const CUtensorMap* m = get_tensor_map(d->b, 2, dims, strides, box);
         if (!m) return TC_ERR_CUDA;
         p.tmB = *m;
     }
 
-    const int stage_bytes = kAStageBytes + BN * 128;
+    const int stage_bytes = kAStageBytes + (pair ? BN / 2 : BN) * 128;
     const int smem_budget = 227 * 1024 - 1024 - 512;
     int stages = smem_budget / stage_bytes;
     if (stages > 8) stages = 8;
@@ -467,16 +504,40 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
     static bool attr_set = false;
     if (!attr_set) {
         int rc = check_cuda(
-            cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-            "cudaFuncSetAttribute(tc_gemm_kernel)");
+            cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+            "cudaFuncSetAttribute(tc_gemm_kernel<false>)");
+        if (rc) return rc;
+        rc = check_cuda(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                        "cudaFuncSetAttribute(tc_gemm_kernel<true>)");
         if (rc) return rc;
         attr_set = true;
     }
-    const long long total_tiles = (long long)p.tiles_m * p.tiles_nn;
-    int grid = sm_count();
-    if (total_tiles < grid) grid = (int)total_tiles;
-    tc_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
-    count_launch();
-    TC_CHECK_LAUNCH("tc_gemm_kernel launch");
+    if (pair) {
+        int units = sm_count() / 2;
+        if (pair_tiles < units) units = (int)pair_tiles;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * units);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int rc = check_cuda(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<true>, p), "tc_gemm_kernel<pair> launch");
+        count_launch();
+        if (rc) return rc;
+    } else {
+        const long long total_tiles = (long long)p.tiles_m * p.tiles_nn;
+        int grid = sm_count();
+        if (total_tiles < grid) grid = (int)total_tiles;
+        tc_gemm_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(p);
+        count_launch();
+        TC_CHECK_LAUNCH("tc_gemm_kernel launch");
+    }
     return TC_OK;
 }
