@@ -1,14 +1,12 @@
 // tooncrafter_b200 — attention kernels.
 //
 //  tc_attention           fused softmax(QK^T)V, head dim 64, tcgen05 MMAs (S = QK^T and O = PV) with TMEM
-//                         accumulators, TMA-staged Q/K/V tiles, fp32 online softmax, one query row per thread.
-//                         Two CTAs per SM: one CTA's softmax overlaps the other's MMAs.
+//                         accumulators, TMA-staged Q/K/V tiles, fp32 online softmax, one query row per thread;
+//                         two query tiles per CTA ping-pong so one tile's softmax overlaps the other's MMAs.
 //  tc_temporal_attention  16-frame temporal self-attention, one (pixel, head) per warp, mma.sync 16x8x16 (HBM-bound).
 //  tc_softmax_rows        row softmax for the unfused d=512 VAE mid-block attention.
 //
 // Reference sites: lvdm/modules/attention.py:81-209,365-412; lvdm/models/autoencoder_dualref.py:172-200,270-341.
-#include <stdlib.h>
-
 #include "tc_common.cuh"
 #include "tc_host.h"
 
@@ -18,8 +16,6 @@ namespace {
 constexpr int kQTile = 128;
 constexpr int kKVTile = 128;
 constexpr int kTileBytes = 128 * 64 * 2;  // 16 KiB: [128 rows][64 halfs], 128B-swizzled
-constexpr int kAttnThreads = 128;
-constexpr int kAttnTmemCols = 256;  // S: cols [0,128), O_blk: cols [128,192)
 
 struct alignas(64) AttnKParams {
     CUtensorMap tmQ;
@@ -43,241 +39,16 @@ __device__ __forceinline__ uint32_t pack_h2(float x, float y) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(kAttnThreads, 2) tc_attn_kernel(const __grid_constant__ AttnKParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sK = smem + kTileBytes;
-    uint8_t* sV = smem + 2 * kTileBytes;
-    uint8_t* sP = smem + 3 * kTileBytes;  // two [128][64] sub-tiles
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * kTileBytes);
-    uint64_t* bar_q = bars + 0;
-    uint64_t* bar_k = bars + 1;
-    uint64_t* bar_v = bars + 2;
-    uint64_t* bar_s = bars + 3;
-    uint64_t* bar_o = bars + 4;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 5);
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int q0 = blockIdx.x * kQTile;
-    const int head = blockIdx.y;
-    const int qb = blockIdx.z;
-    const bool issuer = (tid == 0);
-
-    if (issuer) {
-        tc::tma_prefetch_desc(&p.tmQ);
-        for (int i = 0; i < 5; ++i) tc::mbar_init(&bars[i], 1);
-        tc::fence_mbar_init();
-    }
-    if (warp == 0) {
-        tc::tmem_alloc(tmem_ptr_smem, kAttnTmemCols);
-        tc::tmem_relinquish();
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-    const uint32_t tmem_s = tmem_base;
-    const uint32_t tmem_o = tmem_base + 128;
-    const uint32_t lane_off = ((uint32_t)(warp * 32)) << 16;
-
-    const uint32_t sQ_a = tc::smem_u32(sQ), sK_a = tc::smem_u32(sK), sV_a = tc::smem_u32(sV), sP_a = tc::smem_u32(sP);
-
-    uint32_t ph_k = 0, ph_v = 0, ph_s = 0, ph_o = 0;
-    if (issuer) {
-        tc::mbar_arrive_expect_tx(bar_q, kTileBytes);
-        tc::tma_load_3d(sQ, &p.tmQ, bar_q, head * 64, q0, qb);
-    }
-
-    float o_total[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o_total[i] = 0.f;
-
-    for (int seg = 0; seg < p.n_seg; ++seg) {
-        const int Lk = p.Lk[seg];
-        const int kvb = qb / p.kv_div[seg];
-        const int nblk = (Lk + kKVTile - 1) / kKVTile;
-        const CUtensorMap* tmK = &p.tmK[seg];
-        const CUtensorMap* tmV = &p.tmV[seg];
-
-        if (issuer) {
-            tc::mbar_arrive_expect_tx(bar_k, kTileBytes);
-            tc::tma_load_3d(sK, tmK, bar_k, head * 64, 0, kvb);
-            tc::mbar_arrive_expect_tx(bar_v, kTileBytes);
-            tc::tma_load_3d(sV, tmV, bar_v, head * 64, 0, kvb);
-            if (seg == 0) tc::mbar_wait(bar_q, 0);
-            tc::mbar_wait(bar_k, ph_k);
-            ph_k ^= 1u;
-            tc::tc_fence_after();
-            int nk0 = Lk < kKVTile ? ((Lk + 15) & ~15) : kKVTile;
-            const uint32_t idesc_s = tc::umma_idesc_f16(128, (uint32_t)nk0, 0, 0);
-            const uint64_t qd = tc::umma_desc_sw128(sQ_a), kd = tc::umma_desc_sw128(sK_a);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_f16(tmem_s, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, k != 0);
-            tc::umma_commit(bar_s);
-        }
-
-        float m_run = -INFINITY, l_run = 0.f;
-        float o_acc[64];
-#pragma unroll
-        for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
-
-        for (int j = 0; j < nblk; ++j) {
-            const int kv_left = Lk - j * kKVTile;
-            const int nvalid = kv_left < kKVTile ? kv_left : kKVTile;
-            const int nk = (nvalid + 15) & ~15;  // keys covered by the MMAs of this block
-
-            tc::mbar_wait(bar_s, ph_s);
-            ph_s ^= 1u;
-            tc::tc_fence_after();
-            if (issuer && j + 1 < nblk) {  // S_j done -> K buffer is free
-                tc::mbar_arrive_expect_tx(bar_k, kTileBytes);
-                tc::tma_load_3d(sK, tmK, bar_k, head * 64, (j + 1) * kKVTile, kvb);
-            }
-
-            // ---- pass 1: row max
-            float m_blk = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (c * 16 < nk) {
-                    uint32_t r[16];
-                    tc::tmem_ld16(tmem_s + lane_off + (uint32_t)(c * 16), r);
-                    tc::tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (c * 16 + i < nvalid) m_blk = fmaxf(m_blk, __uint_as_float(r[i]));
-                }
-            }
-            const float m_new = fmaxf(m_run, m_blk);
-            const float m_scaled = m_new * p.scale_log2;
-            const float alpha = fast_exp2(m_run * p.scale_log2 - m_scaled);  // 0 when m_run = -inf
-            // ---- pass 2: p = exp2(s*scale - m*scale), row sum, P tile (fp16, K-major 128B swizzle) to smem
-            float l_blk = 0.f;
-            const int row = tid;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (c * 16 < nk) {
-                    uint32_t r[16];
-                    tc::tmem_ld16(tmem_s + lane_off + (uint32_t)(c * 16), r);
-                    tc::tmem_ld_wait();
-                    float pv[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float e = fast_exp2(__uint_as_float(r[i]) * p.scale_log2 - m_scaled);
-                        pv[i] = (c * 16 + i < nvalid) ? e : 0.f;
-                        l_blk += pv[i];
-                    }
-                    uint4 u0, u1;
-                    __half2 h[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(pv[2 * i], pv[2 * i + 1]);
-                    u0.x = *reinterpret_cast<uint32_t*>(&h[0]);
-                    u0.y = *reinterpret_cast<uint32_t*>(&h[1]);
-                    u0.z = *reinterpret_cast<uint32_t*>(&h[2]);
-                    u0.w = *reinterpret_cast<uint32_t*>(&h[3]);
-                    u1.x = *reinterpret_cast<uint32_t*>(&h[4]);
-                    u1.y = *reinterpret_cast<uint32_t*>(&h[5]);
-                    u1.z = *reinterpret_cast<uint32_t*>(&h[6]);
-                    u1.w = *reinterpret_cast<uint32_t*>(&h[7]);
-                    uint8_t* sub = sP + (c >> 2) * kTileBytes + row * 128;
-                    const int ch0 = (c & 3) * 2;
-                    *reinterpret_cast<uint4*>(sub + (((ch0) ^ (row & 7)) << 4)) = u0;
-                    *reinterpret_cast<uint4*>(sub + (((ch0 + 1) ^ (row & 7)) << 4)) = u1;
-                }
-            }
-            l_run = l_run * alpha + l_blk;
-            m_run = m_new;
-
-            tc::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            tc::tc_fence_before();
-            __syncthreads();
-            if (issuer) {
-                tc::tc_fence_after();
-                tc::mbar_wait(bar_v, ph_v);
-                ph_v ^= 1u;
-                tc::tc_fence_after();
-                const uint32_t idesc_o = tc::umma_idesc_f16(128, 64, 0, 1);  // B (= V tile) is MN-major
-                const uint64_t vd = tc::umma_desc_sw128(sV_a);
-                for (int t = 0; t < nk / 16; ++t) {
-                    const uint64_t pd = tc::umma_desc_sw128(sP_a + (uint32_t)(t >> 2) * kTileBytes) + (uint64_t)((t & 3) * 2);
-                    tc::umma_f16(tmem_o, pd, vd + (uint64_t)(t * 128), idesc_o, t != 0);
-                }
-                tc::umma_commit(bar_o);
-                if (j + 1 < nblk) {
-                    tc::mbar_wait(bar_k, ph_k);
-                    ph_k ^= 1u;
-                    tc::tc_fence_after();
-                    const int left = Lk - (j + 1) * kKVTile;
-                    const int nk1 = left < kKVTile ? ((left + 15) & ~15) : kKVTile;
-                    const uint32_t idesc_s = tc::umma_idesc_f16(128, (uint32_t)nk1, 0, 0);
-                    const uint64_t qd = tc::umma_desc_sw128(sQ_a), kd = tc::umma_desc_sw128(sK_a);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc::umma_f16(tmem_s, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, k != 0);
-                    tc::umma_commit(bar_s);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 64; ++i) o_acc[i] *= alpha;
-
-            tc::mbar_wait(bar_o, ph_o);
-            ph_o ^= 1u;
-            tc::tc_fence_after();
-            if (issuer && j + 1 < nblk) {  // PV_j done -> V buffer is free
-                tc::mbar_arrive_expect_tx(bar_v, kTileBytes);
-                tc::tma_load_3d(sV, tmV, bar_v, head * 64, (j + 1) * kKVTile, kvb);
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t r[16];
-                tc::tmem_ld16(tmem_o + lane_off + (uint32_t)(c * 16), r);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] += __uint_as_float(r[i]);
-            }
-        }
-        const float inv_l = 1.0f / l_run;
-#pragma unroll
-        for (int i = 0; i < 64; ++i) o_total[i] += o_acc[i] * inv_l;
-    }
-
-    const int qrow = q0 + tid;
-    if (qrow < p.Lq) {
-        __half* dst = p.out + ((long long)qb * p.Lq + qrow) * p.ldo + head * 64;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            __half2 h[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(o_total[c * 8 + 2 * i], o_total[c * 8 + 2 * i + 1]);
-            uint4 u;
-            u.x = *reinterpret_cast<uint32_t*>(&h[0]);
-            u.y = *reinterpret_cast<uint32_t*>(&h[1]);
-            u.z = *reinterpret_cast<uint32_t*>(&h[2]);
-            u.w = *reinterpret_cast<uint32_t*>(&h[3]);
-            reinterpret_cast<uint4*>(dst)[c] = u;
-        }
-    }
-
-    tc::tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        tc::tc_fence_after();
-        tc::tmem_dealloc(tmem_base, kAttnTmemCols);
-    }
-}
-
-// ===================================================================================== fused attention v2
 // Ping-pong over TWO query tiles per CTA with specialised warps:
 //   warps 0-3 / 4-7 : softmax warpgroups for query tile 0 / 1 (one query row per thread)
 //   warp 8          : MMA issuer   (S_w = Q_w K^T, O_w = P_w V; tcgen05, accumulators in TMEM)
 //   warp 9          : TMA producer (Q tiles once, K / V tiles double-buffered)
 // While one warpgroup runs its softmax (MUFU/ALU bound) the tensor core works on the other tile's MMAs.
-constexpr int kAttn2Threads = 320;
-constexpr int kAttn2TmemCols = 512;  // S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
+constexpr int kAttnThreads = 320;
+constexpr int kAttnTmemCols = 512;  // S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
 
 template <bool kTwoSeg>
-__global__ void __launch_bounds__(kAttn2Threads, 1) tc_attn2_kernel(const __grid_constant__ AttnKParams p) {
+__global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_constant__ AttnKParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                     // 2 tiles
@@ -317,7 +88,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) tc_attn2_kernel(const __grid
         tc::fence_mbar_init();
     }
     if (warp == 8) {
-        tc::tmem_alloc(tmem_ptr_smem, kAttn2TmemCols);
+        tc::tmem_alloc(tmem_ptr_smem, kAttnTmemCols);
         tc::tmem_relinquish();
     }
     tc::tc_fence_before();
@@ -582,7 +353,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) tc_attn2_kernel(const __grid
     __syncthreads();
     if (warp == 8) {
         tc::tc_fence_after();
-        tc::tmem_dealloc(tmem_base, kAttn2TmemCols);
+        tc::tmem_dealloc(tmem_base, kAttnTmemCols);
     }
 }
 
@@ -891,43 +662,26 @@ extern "C" int tc_attention(const TcAttention* d, void* stream_v) {
     p.out = reinterpret_cast<__half*>(d->out);
     p.ldo = d->ldo;
     p.scale_log2 = d->scale * 1.4426950408889634f;
-    static const bool use_v1 = (getenv("TC_ATTN_V1") != nullptr);   // A/B switch during bring-up
-    if (use_v1) {
-        const size_t smem_bytes = 5 * kTileBytes + 1024 + 128;
-        static bool attr_set = false;
-        if (!attr_set) {
-            int rc = check_cuda(
-                cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
-                "cudaFuncSetAttribute(tc_attn_kernel)");
-            if (rc) return rc;
-            attr_set = true;
-        }
-        dim3 grid((d->Lq + kQTile - 1) / kQTile, d->heads, d->q_batches);
-        tc_attn_kernel<<<grid, kAttnThreads, smem_bytes, stream>>>(p);
-        count_launch();
-        TC_CHECK_LAUNCH("tc_attn_kernel");
-        return TC_OK;
-    }
     const size_t smem_bytes = 10 * kTileBytes + 1024 + 256;
     static bool attr2_set = false;
     if (!attr2_set) {
-        int rc = check_cuda(cudaFuncSetAttribute(tc_attn2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        int rc = check_cuda(cudaFuncSetAttribute(tc_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)smem_bytes),
-                            "cudaFuncSetAttribute(tc_attn2_kernel<false>)");
+                            "cudaFuncSetAttribute(tc_attn_kernel<false>)");
         if (rc) return rc;
-        rc = check_cuda(cudaFuncSetAttribute(tc_attn2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        rc = check_cuda(cudaFuncSetAttribute(tc_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem_bytes),
-                        "cudaFuncSetAttribute(tc_attn2_kernel<true>)");
+                        "cudaFuncSetAttribute(tc_attn_kernel<true>)");
         if (rc) return rc;
         attr2_set = true;
     }
     dim3 grid((d->Lq + 2 * kQTile - 1) / (2 * kQTile), d->heads, d->q_batches);
     if (d->n_seg == 2)
-        tc_attn2_kernel<true><<<grid, kAttn2Threads, smem_bytes, stream>>>(p);
+        tc_attn_kernel<true><<<grid, kAttnThreads, smem_bytes, stream>>>(p);
     else
-        tc_attn2_kernel<false><<<grid, kAttn2Threads, smem_bytes, stream>>>(p);
+        tc_attn_kernel<false><<<grid, kAttnThreads, smem_bytes, stream>>>(p);
     count_launch();
-    TC_CHECK_LAUNCH("tc_attn2_kernel");
+    TC_CHECK_LAUNCH("tc_attn_kernel");
     return TC_OK;
 }
 

@@ -253,6 +253,14 @@ class DDIMSampler(object):
             model_output = e_uc + unconditional_guidance_scale * (e_c - e_uc)
             if guidance_rescale > 0.0:
                 model_output = rescale_noise_cfg(model_output, e_c, guidance_rescale=guidance_rescale)
+        return self._ddim_update(x, t, index, model_output, c, repeat_noise, use_original_steps, quantize_denoised,
+                                 temperature, noise_dropout, score_corrector, corrector_kwargs)
+
+    def _ddim_update(self, x, t, index, model_output, c, repeat_noise, use_original_steps, quantize_denoised,
+                     temperature, noise_dropout, score_corrector, corrector_kwargs):
+        """ddim.py:231-277: v -> (eps, x0), dynamic rescale, x_{t-1}."""
+        m = self.model
+        b, device = x.shape[0], x.device
         e_t = m.predict_eps_from_z_and_v(x, t, model_output) if m.parameterization == "v" else model_output
         if score_corrector is not None:
             assert m.parameterization == "eps", "not implemented"
@@ -281,3 +289,32 @@ class DDIMSampler(object):
         if noise_dropout > 0.0:
             noise = torch.nn.functional.dropout(noise, p=noise_dropout)
         return a_prev.sqrt() * pred_x0 + dir_xt + noise, pred_x0
+
+
+class DDIMSamplerMultiCond(DDIMSampler):
+    """lvdm/models/samplers/ddim_multiplecond.py:10-320 — three-way guidance (text / image-without-text / uncond):
+    v = e_uc + cfg_img * (e_img - e_uc) + s * (e_c - e_img)  (:229-234).  Each term is one pass through the CUDA UNet
+    engine; the update itself follows the general path."""
+
+    def _fast_path_ok(self, *a, **k):
+        return False
+
+    @torch.no_grad()
+    def p_sample_ddim(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,
+                      temperature=1.0, noise_dropout=0.0, score_corrector=None, corrector_kwargs=None,
+                      unconditional_guidance_scale=1.0, unconditional_conditioning=None, uc_type=None, cfg_img=None,
+                      mask=None, x0=None, guidance_rescale=0.0, **kwargs):
+        m = self.model
+        cfg_img = unconditional_guidance_scale if cfg_img is None else cfg_img
+        uc_img = kwargs["unconditional_conditioning_img_nonetext"]
+        if unconditional_conditioning is None or unconditional_guidance_scale == 1.0:
+            model_output = m.apply_model(x, t, c, **kwargs)
+        else:
+            e_c = m.apply_model(x, t, c, **kwargs).clone()
+            e_uc = m.apply_model(x, t, unconditional_conditioning, **kwargs).clone()
+            e_img = m.apply_model(x, t, uc_img, **kwargs)
+            model_output = e_uc + cfg_img * (e_img - e_uc) + unconditional_guidance_scale * (e_c - e_img)
+            if guidance_rescale > 0.0:
+                model_output = rescale_noise_cfg(model_output, e_c, guidance_rescale=guidance_rescale)
+        return self._ddim_update(x, t, index, model_output, c, repeat_noise, use_original_steps, quantize_denoised,
+                                 temperature, noise_dropout, score_corrector, corrector_kwargs)
