@@ -98,29 +98,37 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
 
     if (warp == 9) {
         // ------------------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        // whole warp converged, one elected lane issues (see tc_gemm.cu for why `if (lane == 0)` is slow)
+        if (tc::elect_one()) {
             tc::tma_prefetch_desc(&p.tmQ);
             tc::mbar_arrive_expect_tx(bar_q, (uint32_t)(ntiles * kTileBytes));
             for (int w = 0; w < ntiles; ++w) tc::tma_load_3d(sQ + w * kTileBytes, &p.tmQ, bar_q, head * 64, q0 + w * kQTile, qb);
-            int g = 0;
-            for (int seg = 0; seg < p.n_seg; ++seg) {
-                const int nblk = (p.Lk[seg] + kKVTile - 1) / kKVTile;
-                const int kvb = qb / p.kv_div[seg];
-                for (int j = 0; j < nblk; ++j, ++g) {
-                    const int st = g & 1;
-                    const uint32_t ph = (uint32_t)((g >> 1) & 1);
-                    tc::mbar_wait(&k_free[st], ph ^ 1u);
+        }
+        __syncwarp();
+        int g = 0;
+        for (int seg = 0; seg < p.n_seg; ++seg) {
+            const int nblk = (p.Lk[seg] + kKVTile - 1) / kKVTile;
+            const int kvb = qb / p.kv_div[seg];
+            for (int j = 0; j < nblk; ++j, ++g) {
+                const int st = g & 1;
+                const uint32_t ph = (uint32_t)((g >> 1) & 1);
+                tc::mbar_wait(&k_free[st], ph ^ 1u);
+                if (tc::elect_one()) {
                     tc::mbar_arrive_expect_tx(&k_full[st], kTileBytes);
                     tc::tma_load_3d(sK + st * kTileBytes, &p.tmK[seg], &k_full[st], head * 64, j * kKVTile, kvb);
-                    tc::mbar_wait(&v_free[st], ph ^ 1u);
+                }
+                __syncwarp();
+                tc::mbar_wait(&v_free[st], ph ^ 1u);
+                if (tc::elect_one()) {
                     tc::mbar_arrive_expect_tx(&v_full[st], kTileBytes);
                     tc::tma_load_3d(sV + st * kTileBytes, &p.tmV[seg], &v_full[st], head * 64, j * kKVTile, kvb);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 8) {
         // ------------------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        {
             const uint32_t sQ_a = tc::smem_u32(sQ), sK_a = tc::smem_u32(sK), sV_a = tc::smem_u32(sV), sP_a = tc::smem_u32(sP);
             int G = 0;
             for (int seg = 0; seg < p.n_seg; ++seg) G += (p.Lk[seg] + kKVTile - 1) / kKVTile;
@@ -136,24 +144,26 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
                 const int left = p.Lk[seg] - j * kKVTile;
                 return left < kKVTile ? ((left + 15) & ~15) : kKVTile;
             };
-            auto issue_s = [&](int w, int st, int nk) {
+            // S_w = Q_w K^T for key block in stage `st` (+ the commits that follow it); called by ONE elected lane
+            auto issue_s = [&](int w, int st, int nk, bool last_tile) {
                 const uint32_t idesc = tc::umma_idesc_f16(128, (uint32_t)nk, 0, 0);
                 const uint64_t qd = tc::umma_desc_sw128(sQ_a + (uint32_t)w * kTileBytes);
                 const uint64_t kd = tc::umma_desc_sw128(sK_a + (uint32_t)st * kTileBytes);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     tc::umma_f16(tmem_base + (uint32_t)w * 128, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc, k != 0);
+                tc::umma_commit(&s_full[w]);
+                if (last_tile) tc::umma_commit(&k_free[st]);
             };
             tc::mbar_wait(bar_q, 0);
             tc::mbar_wait(&k_full[0], 0);
             tc::tc_fence_after();
             {
                 const int nk = block_nk(0);
-                for (int w = 0; w < ntiles; ++w) {
-                    issue_s(w, 0, nk);
-                    tc::umma_commit(&s_full[w]);
+                if (tc::elect_one()) {
+                    for (int w = 0; w < ntiles; ++w) issue_s(w, 0, nk, w == ntiles - 1);
                 }
-                tc::umma_commit(&k_free[0]);
+                __syncwarp();
             }
             for (int g = 0; g < G; ++g) {
                 const int st = g & 1;
@@ -162,25 +172,20 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
                 for (int w = 0; w < ntiles; ++w) {
                     tc::mbar_wait(&p_ready[w], (uint32_t)(g & 1));
                     if (w == 0) tc::mbar_wait(&v_full[st], (uint32_t)((g >> 1) & 1));
+                    if (g + 1 < G && w == 0) tc::mbar_wait(&k_full[(g + 1) & 1], (uint32_t)(((g + 1) >> 1) & 1));
                     tc::tc_fence_after();
-                    const uint32_t idesc_o = tc::umma_idesc_f16(128, 64, 0, 1);  // B (= V tile) MN-major
-                    const uint64_t vd = tc::umma_desc_sw128(sV_a + (uint32_t)st * kTileBytes);
-                    for (int t = 0; t < nk / 16; ++t) {
-                        const uint64_t pd = tc::umma_desc_sw128(sP_a + (uint32_t)(2 * w + (t >> 2)) * kTileBytes) + (uint64_t)((t & 3) * 2);
-                        tc::umma_f16(tmem_base + 256 + (uint32_t)w * 64, pd, vd + (uint64_t)(t * 128), idesc_o, t != 0);
-                    }
-                    tc::umma_commit(&o_full[w]);
-                    if (w == ntiles - 1) tc::umma_commit(&v_free[st]);
-                    if (g + 1 < G) {
-                        const int st1 = (g + 1) & 1;
-                        if (w == 0) {
-                            tc::mbar_wait(&k_full[st1], (uint32_t)(((g + 1) >> 1) & 1));
-                            tc::tc_fence_after();
+                    if (tc::elect_one()) {
+                        const uint32_t idesc_o = tc::umma_idesc_f16(128, 64, 0, 1);  // B (= V tile) MN-major
+                        const uint64_t vd = tc::umma_desc_sw128(sV_a + (uint32_t)st * kTileBytes);
+                        for (int t = 0; t < nk / 16; ++t) {
+                            const uint64_t pd = tc::umma_desc_sw128(sP_a + (uint32_t)(2 * w + (t >> 2)) * kTileBytes) + (uint64_t)((t & 3) * 2);
+                            tc::umma_f16(tmem_base + 256 + (uint32_t)w * 64, pd, vd + (uint64_t)(t * 128), idesc_o, t != 0);
                         }
-                        issue_s(w, st1, nk_next);
-                        tc::umma_commit(&s_full[w]);
-                        if (w == ntiles - 1) tc::umma_commit(&k_free[st1]);
+                        tc::umma_commit(&o_full[w]);
+                        if (w == ntiles - 1) tc::umma_commit(&v_free[st]);
+                        if (g + 1 < G) issue_s(w, (g + 1) & 1, nk_next, w == ntiles - 1);
                     }
+                    __syncwarp();
                 }
             }
         }

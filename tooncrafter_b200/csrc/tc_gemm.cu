@@ -145,7 +145,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        // The whole warp walks the loop converged and one ELECTED lane issues: a plain `if (lane == 0)` makes the
+        // issue code thread-divergent and ptxas wraps every TMA / MMA in ELECT + R2UR.BROADCAST + BRA.U.ANY sequences
+        // (measured: ~550 cycles of issue latency per k-block, the kernel's bottleneck in profiles/r01_*conv320*).
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = unit; tile < total_tiles; tile += n_units) {
@@ -155,19 +158,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap], an = n0 + p.tap_dn[tap];
                     for (int kc = 0; kc < p.kc_per_tap; ++kc) {
                         tc::mbar_wait(&empty_bar[stage], phase ^ 1u);
-                        uint8_t* dA = sA + (size_t)stage * kAStageBytes;
-                        uint8_t* dB = sB + (size_t)stage * b_stage_bytes;
-                        const int kcol = (tap * p.kc_per_tap + kc) * kBlockK;
-                        if constexpr (kPair) {
-                            // both CTAs' bytes are credited to the leader's barrier
-                            if (rank == 0) tc::mbar_arrive_expect_tx(&full_bar[stage], 2u * (p.a_bytes + b_stage_bytes));
-                            tc::tma_load_4d_pair(dA, &p.tmA, &full_bar[stage], kc * kBlockK, ax, ay, an);
-                            tc::tma_load_2d_pair(dB, &p.tmB, &full_bar[stage], kcol, nt * BN + (int)rank * b_rows);
-                        } else {
-                            tc::mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + b_stage_bytes);
-                            tc::tma_load_4d(dA, &p.tmA, &full_bar[stage], kc * kBlockK, ax, ay, an);
-                            tc::tma_load_2d(dB, &p.tmB, &full_bar[stage], kcol, nt * BN);
+                        if (tc::elect_one()) {
+                            uint8_t* dA = sA + (size_t)stage * kAStageBytes;
+                            uint8_t* dB = sB + (size_t)stage * b_stage_bytes;
+                            const int kcol = (tap * p.kc_per_tap + kc) * kBlockK;
+                            if constexpr (kPair) {
+                                // both CTAs' bytes are credited to the leader's barrier
+                                if (rank == 0) tc::mbar_arrive_expect_tx(&full_bar[stage], 2u * (p.a_bytes + b_stage_bytes));
+                                tc::tma_load_4d_pair(dA, &p.tmA, &full_bar[stage], kc * kBlockK, ax, ay, an);
+                                tc::tma_load_2d_pair(dB, &p.tmB, &full_bar[stage], kcol, nt * BN + (int)rank * b_rows);
+                            } else {
+                                tc::mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + b_stage_bytes);
+                                tc::tma_load_4d(dA, &p.tmA, &full_bar[stage], kc * kBlockK, ax, ay, an);
+                                tc::tma_load_2d(dB, &p.tmB, &full_bar[stage], kcol, nt * BN);
+                            }
                         }
+                        __syncwarp();
                         if (++stage == S) {
                             stage = 0;
                             phase ^= 1u;
@@ -178,9 +184,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {
             const uint32_t idesc = tc::umma_idesc_f16(kPair ? 2 * kBlockM : kBlockM, (uint32_t)BN, 0, 0);
-            const uint32_t sA_addr = tc::smem_u32(sA), sB_addr = tc::smem_u32(sB);
+            const uint64_t a_desc0 = tc::umma_desc_sw128(tc::smem_u32(sA));
+            const uint64_t b_desc0 = tc::umma_desc_sw128(tc::smem_u32(sB));
+            const uint64_t a_step = (uint64_t)(kAStageBytes >> 4), b_step = (uint64_t)(b_stage_bytes >> 4);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -192,25 +200,31 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 for (int kb = 0; kb < kblocks; ++kb) {
                     tc::mbar_wait(&full_bar[stage], phase);
                     tc::tc_fence_after();
-                    const uint64_t a_desc = tc::umma_desc_sw128(sA_addr + (uint32_t)stage * kAStageBytes);
-                    const uint64_t b_desc = tc::umma_desc_sw128(sB_addr + (uint32_t)stage * b_stage_bytes);
+                    if (tc::elect_one()) {
+                        const uint64_t a_desc = a_desc0 + a_step * (uint64_t)stage;
+                        const uint64_t b_desc = b_desc0 + b_step * (uint64_t)stage;
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        // advance 16 halfs = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
-                        if constexpr (kPair)
-                            tc::umma_f16_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                                              (kb | k) != 0 ? 1u : 0u);
-                        else
-                            tc::umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                                         (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            // advance 16 halfs = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
+                            if constexpr (kPair)
+                                tc::umma_f16_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                                  (kb | k) != 0 ? 1u : 0u);
+                            else
+                                tc::umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                             (kb | k) != 0 ? 1u : 0u);
+                        }
+                        if constexpr (kPair) tc::umma_commit_pair(&empty_bar[stage]); else tc::umma_commit(&empty_bar[stage]);
                     }
-                    if constexpr (kPair) tc::umma_commit_pair(&empty_bar[stage]); else tc::umma_commit(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == S) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                if constexpr (kPair) tc::umma_commit_pair(&tfull_bar[acc]); else tc::umma_commit(&tfull_bar[acc]);
+                if (tc::elect_one()) {
+                    if constexpr (kPair) tc::umma_commit_pair(&tfull_bar[acc]); else tc::umma_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
