@@ -48,7 +48,8 @@ int tc_sm_count(void);
  *
  * with m = (n*oH + y)*oW + x over the output pixel grid [oN][oH][oW]; A reads outside [a_N][a_H][a_W]
  * are zero (TMA out-of-bounds fill == the conv's zero padding).
- * epilogue: v = acc + bias[j] + bias2[m / bias2_rows_per][j];  v = v*acc_scale + res[m][j];  (GEGLU optional)
+ * epilogue: a = ln_stats ? rstd_m*(acc - mean_m*ln_u[j]) : acc;  v = a + bias[j] + bias2[m / bias2_rows_per][j];
+ *           v = v*acc_scale + res[m][j];  (GEGLU optional)
  *
  * Replaces (reference call sites): nn.Conv2d 3x3 / 1x1 (openaimodel3d.py:68,96,154,179,187,386,545;
  * autoencoder_dualref.py:52-69,914-935), nn.Conv3d (3,1,1) (openaimodel3d.py:255-266; autoencoder_dualref.py
@@ -82,6 +83,11 @@ typedef struct {
   float acc_scale;     /* 1.0f for plain layers */
   int flags;
   int block_n;         /* 0 = auto */
+  /* folded LayerNorm of the A operand (attention.py:225-227,243-245): with Wt pre-multiplied by gamma,
+   * LN(x) @ W^T = rstd_m * (acc - mean_m * ln_u[j]) (+ bias' = beta @ W^T + b).  ln_stats = {mean, rstd} per output
+   * row from tc_row_stats, ln_u[j] = sum_k Wt[j][k].  Both NULL for plain layers. */
+  const float* ln_stats; /* [M][2] */
+  const float* ln_u;     /* [n_cols] */
 } TcConvGemm;
 
 int tc_conv_gemm(const TcConvGemm* desc, void* stream);
@@ -98,6 +104,10 @@ int tc_conv_gemm(const TcConvGemm* desc, void* stream);
 int tc_groupnorm(const void* x, long long ldx, void* y, long long ldy, const float* gamma, const float* beta,
                  int frames, int frames_per_stat, int hw, int C, int G, float eps, int silu, float* ws,
                  void* stream);
+
+/* per-row {mean, rstd} of [rows][C] halfs (the statistics half of nn.LayerNorm, attention.py:225-227); the
+ * normalisation itself is folded into the consuming tc_conv_gemm (ln_stats / ln_u). */
+int tc_row_stats(const void* x, long long ldx, int rows, int C, float eps, float* stats, void* stream);
 
 /* LayerNorm over the last dim of [rows][C] halfs (attention.py:225-227), fp32 math, fp16 out. */
 int tc_layernorm(const void* x, long long ldx, void* y, long long ldy, const float* gamma, const float* beta,

@@ -25,7 +25,7 @@ def _view2d(t, rows, cols, ld, off):
 
 def conv_gemm(a, a_dims, a_strides, w, taps, out, out_dims, n_cols, *, ldc=None, bias=None, bias2=None,
               bias2_rows_per=0, res=None, ldr=None, acc_scale=1.0, geglu=False, block_n=0, a_offset=0,
-              out_offset=0, res_offset=0):
+              out_offset=0, res_offset=0, ln_stats=None, ln_u=None):
     aN, aH, aW, C = a_dims
     sN, sH, sW = a_strides
     A = _strided(a, (aN, aH, aW, C), (sN, sH, sW, 1), a_offset).float()
@@ -44,6 +44,9 @@ def conv_gemm(a, a_dims, a_strides, w, taps, out, out_dims, n_cols, *, ldc=None,
     assert w.shape[1] == len(taps) * C, f"weight K {w.shape[1]} != taps*C {len(taps) * C}"
     assert n_cols <= w.shape[0]
     acc = X @ w[:n_cols].float().t()
+    if ln_stats is not None:
+        st = ln_stats.view(-1, 2)[:M].float()
+        acc = st[:, 1:2] * (acc - st[:, 0:1] * ln_u[:n_cols].float())
     if bias is not None:
         acc = acc + bias[:n_cols].float()
     if geglu:
@@ -76,6 +79,13 @@ def groupnorm(x, y, gamma, beta, *, frames, frames_per_stat, hw, C, G=32, eps=1e
     if silu:
         o = F.silu(o)
     _view2d(y, rows, C, ldy, y_offset).copy_(o.permute(0, 2, 1).reshape(rows, C).half())
+
+
+def row_stats(x, stats, *, rows, C, eps=1e-5, ldx=None):
+    X = _view2d(x, rows, C, ldx if ldx is not None else C, 0).float()
+    mean = X.mean(1)
+    var = X.var(1, unbiased=False)
+    stats.view(-1, 2)[:rows] = torch.stack([mean, torch.rsqrt(var + eps)], 1)
 
 
 def layernorm(x, y, gamma, beta, *, rows, C, eps=1e-5, ldx=None, ldy=None):
@@ -183,7 +193,7 @@ def ddim_step(e_c, e_uc, x, noise, x_prev, pred_x0, coef, ws, *, B, n):
     x_prev.reshape(B, n).copy_(sqrt_aprev * x0 + dir_coef * eps + sigma * nz)
 
 
-_TABLE = {f.__name__: f for f in (conv_gemm, groupnorm, layernorm, attention, temporal_attention, softmax_rows,
+_TABLE = {f.__name__: f for f in (conv_gemm, groupnorm, row_stats, layernorm, attention, temporal_attention, softmax_rows,
                                   ncthw_to_cl, cl_to_ncthw, upsample2x, phase_split2, copy2d, add2d, time_embed,
                                   small_linear, ddim_step)}
 

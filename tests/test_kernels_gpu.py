@@ -94,6 +94,31 @@ def test_linear_geglu(ops):
     _close(out, ref, "geglu")
 
 
+@pytest.mark.parametrize("rows,C,N,geglu", [(1000, 320, 960, False), (300, 640, 640, False), (2560, 320, 2560, True)])
+def test_linear_with_folded_layernorm(ops, rows, C, N, geglu):
+    """tc_row_stats + GEMM epilogue  ==  Linear(LayerNorm(x))  (attention.py:243-245 with norm folded into the GEMM)."""
+    from tooncrafter_b200 import engine
+    x = (_rand(rows, C, seed=55) * 3 + 0.7).half()
+    ln = torch.nn.LayerNorm(C).to(DEV)
+    with torch.no_grad():
+        ln.weight.copy_(_rand(C, seed=56) * 0.2 + 1.0)
+        ln.bias.copy_(_rand(C, seed=57) * 0.2)
+    w = _rand(N, C, scale=C ** -0.5, seed=58)
+    b = _rand(N, seed=59)
+    perm = engine.geglu_perm(N).to(DEV) if geglu else None
+    f = engine.fold_layernorm(w, b, ln, torch.device(DEV), perm=perm)
+    stats = torch.zeros(rows, 2, device=DEV)
+    ops.row_stats(x, stats, rows=rows, C=C)
+    ref_mean = x.float().mean(1)
+    assert (stats[:, 0] - ref_mean).abs().max().item() < 1e-4
+    out = torch.zeros(rows, N // 2 if geglu else N, dtype=torch.float16, device=DEV)
+    ops.linear(x, f.w, out, rows=rows, K=C, n_cols=N, bias=f.c, ln_stats=stats, ln_u=f.u, geglu=geglu,
+               block_n=256 if geglu else 0)
+    h = F.linear(F.layer_norm(x.float(), (C,), ln.weight, ln.bias, 1e-5), w, b)
+    ref = h[:, :N // 2] * F.gelu(h[:, N // 2:]) if geglu else h
+    _close(out, ref, "linear with folded LayerNorm", rel=4e-3, abs_=2e-3)
+
+
 @pytest.mark.parametrize("N,H,W,Cin,Cout", [(4, 20, 32, 128, 192), (6, 5, 8, 256, 320), (2, 40, 64, 64, 320),
                                              (3, 10, 16, 320, 4), (1, 16, 256, 128, 128)])
 def test_conv3x3(ops, N, H, W, Cin, Cout):

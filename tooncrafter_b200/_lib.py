@@ -40,6 +40,8 @@ class TcConvGemm(C.Structure):
         ("acc_scale", C.c_float),
         ("flags", C.c_int),
         ("block_n", C.c_int),
+        ("ln_stats", C.c_void_p),
+        ("ln_u", C.c_void_p),
     ]
 
 
@@ -63,6 +65,7 @@ _PROTOTYPES = {
     "tc_groupnorm": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p,
                                C.c_void_p]),
+    "tc_row_stats": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "tc_layernorm": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "tc_attention": (C.c_int, [C.POINTER(TcAttention), C.c_void_p]),

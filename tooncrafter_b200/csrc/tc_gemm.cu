@@ -50,6 +50,8 @@ struct alignas(64) GemmKParams {
     long long ldr;
     float acc_scale;
     int flags;
+    const float2* ln_stats;  // per output row {mean, rstd} (folded LayerNorm) or null
+    const float* ln_u;       // per column sum_k Wt[j][k]
 };
 
 __device__ __forceinline__ void store_row16(__half* dst, const float (&v)[16], int ncols_valid) {
@@ -256,6 +258,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             const long long m = ((long long)n * p.oH + y) * p.oW + x;
             const __half* rrow = (p.res && row_ok) ? p.res + m * p.ldr + (long long)nt * BN : nullptr;
 
+            float ln_mean = 0.f, ln_rstd = 1.f;
+            if (p.ln_stats && row_ok) {
+                const float2 st = __ldg(p.ln_stats + m);
+                ln_mean = st.x;
+                ln_rstd = st.y;
+            }
             // ---- residual prefetch (up to 128 columns = 16 x 16 B per thread)
             uint4 rres[16];
             if (rrow && vec_ok) {
@@ -288,6 +296,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
                     if (vec_ok) {
+                        if (p.ln_u) {
+                            const float* urow = p.ln_u + (long long)nt * BN + c;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 u4 = __ldg(reinterpret_cast<const float4*>(urow) + i);
+                                v[4 * i] = ln_rstd * (v[4 * i] - ln_mean * u4.x);
+                                v[4 * i + 1] = ln_rstd * (v[4 * i + 1] - ln_mean * u4.y);
+                                v[4 * i + 2] = ln_rstd * (v[4 * i + 2] - ln_mean * u4.z);
+                                v[4 * i + 3] = ln_rstd * (v[4 * i + 3] - ln_mean * u4.w);
+                            }
+                        }
                         if (brow) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
@@ -357,6 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     tc::tmem_ld_wait();
                     if (!row_ok) continue;
                     float v[16];
+                    const float* urow = p.ln_u ? p.ln_u + (long long)nt * BN : nullptr;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
@@ -364,13 +384,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                             ba = __ldg(reinterpret_cast<const float4*>(brow + c) + i);
                             bg = __ldg(reinterpret_cast<const float4*>(brow + half_bn + c) + i);
                         }
-                        v[4 * i] = (__uint_as_float(ra[4 * i]) + ba.x) * tc::gelu_erf_f(__uint_as_float(rg[4 * i]) + bg.x);
-                        v[4 * i + 1] =
-                            (__uint_as_float(ra[4 * i + 1]) + ba.y) * tc::gelu_erf_f(__uint_as_float(rg[4 * i + 1]) + bg.y);
-                        v[4 * i + 2] =
-                            (__uint_as_float(ra[4 * i + 2]) + ba.z) * tc::gelu_erf_f(__uint_as_float(rg[4 * i + 2]) + bg.z);
-                        v[4 * i + 3] =
-                            (__uint_as_float(ra[4 * i + 3]) + ba.w) * tc::gelu_erf_f(__uint_as_float(rg[4 * i + 3]) + bg.w);
+                        float a0 = __uint_as_float(ra[4 * i]), a1 = __uint_as_float(ra[4 * i + 1]);
+                        float a2 = __uint_as_float(ra[4 * i + 2]), a3 = __uint_as_float(ra[4 * i + 3]);
+                        float g0 = __uint_as_float(rg[4 * i]), g1 = __uint_as_float(rg[4 * i + 1]);
+                        float g2 = __uint_as_float(rg[4 * i + 2]), g3 = __uint_as_float(rg[4 * i + 3]);
+                        if (urow) {
+                            const float4 ua = __ldg(reinterpret_cast<const float4*>(urow + c) + i);
+                            const float4 ug = __ldg(reinterpret_cast<const float4*>(urow + half_bn + c) + i);
+                            a0 = ln_rstd * (a0 - ln_mean * ua.x);
+                            a1 = ln_rstd * (a1 - ln_mean * ua.y);
+                            a2 = ln_rstd * (a2 - ln_mean * ua.z);
+                            a3 = ln_rstd * (a3 - ln_mean * ua.w);
+                            g0 = ln_rstd * (g0 - ln_mean * ug.x);
+                            g1 = ln_rstd * (g1 - ln_mean * ug.y);
+                            g2 = ln_rstd * (g2 - ln_mean * ug.z);
+                            g3 = ln_rstd * (g3 - ln_mean * ug.w);
+                        }
+                        v[4 * i] = (a0 + ba.x) * tc::gelu_erf_f(g0 + bg.x);
+                        v[4 * i + 1] = (a1 + ba.y) * tc::gelu_erf_f(g1 + bg.y);
+                        v[4 * i + 2] = (a2 + ba.z) * tc::gelu_erf_f(g2 + bg.z);
+                        v[4 * i + 3] = (a3 + ba.w) * tc::gelu_erf_f(g3 + bg.w);
                     }
                     store_row16(orow + c, v, 16);
                 }
@@ -418,6 +451,8 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
                  "tc_conv_gemm: operands must be 16-byte aligned");
     TC_CHECK_ARG(d->a_sW % 8 == 0 && d->a_sH % 8 == 0 && d->a_sN % 8 == 0 && d->ldb % 8 == 0 && d->ldc % 8 == 0,
                  "tc_conv_gemm: strides must be multiples of 8 elements");
+    TC_CHECK_ARG((d->ln_stats == nullptr) == (d->ln_u == nullptr), "tc_conv_gemm: ln_stats and ln_u go together");
+    TC_CHECK_ARG(!d->ln_stats || d->n_cols % 16 == 0, "tc_conv_gemm: folded LayerNorm needs n_cols % 16 == 0");
     TC_CHECK_ARG(!d->res || (d->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(d->res) & 15) == 0),
                  "tc_conv_gemm: residual must be 16-byte aligned");
     const bool geglu = (d->flags & TC_EPI_GEGLU) != 0;
@@ -483,6 +518,8 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
     p.ldr = d->ldr;
     p.acc_scale = d->acc_scale;
     p.flags = d->flags;
+    p.ln_stats = reinterpret_cast<const float2*>(d->ln_stats);
+    p.ln_u = d->ln_u;
 
     // --- tensor maps
     {

@@ -226,7 +226,68 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, long long ldx, __
     }
 }
 
+// ---- LayerNorm statistics only: (mean, rstd) per row; the normalisation is folded into the consuming GEMM ----
+template <int kMaxVec>
+__global__ void row_stats_kernel(const __half* __restrict__ x, long long ldx, int rows, int C, float eps,
+                                 float2* __restrict__ stats) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int V = C >> 3;
+    const __half* xr = x + (long long)warp * ldx;
+    float f[kMaxVec][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+        const int v = lane + 32 * i;
+        if (v < V) {
+            const uint4 u = *reinterpret_cast<const uint4*>(xr + v * 8);
+            unpack8(u, f[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sum += f[i][j];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+        const int v = lane + 32 * i;
+        if (v < V) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = f[i][j] - mean;
+                sq += d * d;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (lane == 0) stats[warp] = make_float2(mean, rsqrtf(sq / (float)C + eps));
+}
+
 }  // namespace
+
+extern "C" int tc_row_stats(const void* x, long long ldx, int rows, int C, float eps, float* stats, void* stream_v) {
+    using namespace tc_host;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    TC_CHECK_ARG(x && stats, "tc_row_stats: null pointer");
+    TC_CHECK_ARG(C > 0 && C % 8 == 0 && C <= 2048 && ldx % 8 == 0 && rows > 0, "tc_row_stats: bad shape");
+    const int threads = 256;
+    const int blocks = (rows + 7) / 8;
+    const __half* xp = reinterpret_cast<const __half*>(x);
+    float2* sp = reinterpret_cast<float2*>(stats);
+    if (C <= 512)
+        row_stats_kernel<2><<<blocks, threads, 0, stream>>>(xp, ldx, rows, C, eps, sp);
+    else if (C <= 1280)
+        row_stats_kernel<5><<<blocks, threads, 0, stream>>>(xp, ldx, rows, C, eps, sp);
+    else
+        row_stats_kernel<8><<<blocks, threads, 0, stream>>>(xp, ldx, rows, C, eps, sp);
+    count_launch();
+    TC_CHECK_LAUNCH("row_stats_kernel");
+    return TC_OK;
+}
 
 extern "C" int tc_groupnorm(const void* x, long long ldx, void* y, long long ldy, const float* gamma,
                             const float* beta, int frames, int frames_per_stat, int hw, int C, int G, float eps,

@@ -50,17 +50,28 @@ def pack_linear(w: torch.Tensor, dev) -> torch.Tensor:
     return _h(w.reshape(w.shape[0], -1), dev)
 
 
-def pack_geglu(w: torch.Tensor, b: torch.Tensor, dev, bn: int = GEGLU_BN):
-    """GEGLU.proj [2*inner, dim] (rows: value half then gate half, attention.py:421) -> per-N-tile interleave
-    [a(bn/2) | gate(bn/2)] so one accumulator tile holds matching value/gate columns."""
-    inner = w.shape[0] // 2
+def geglu_perm(n2: int, bn: int = GEGLU_BN) -> torch.Tensor:
+    """Row permutation of GEGLU.proj [2*inner, dim] (rows: value half then gate half, attention.py:421) into the
+    per-N-tile interleave [value(bn/2) | gate(bn/2)], so one accumulator tile holds matching value/gate columns."""
+    inner = n2 // 2
     hb = bn // 2
     assert inner % hb == 0, f"GEGLU inner dim {inner} must be a multiple of {hb}"
-    wa, wg = w[:inner].reshape(inner // hb, hb, -1), w[inner:].reshape(inner // hb, hb, -1)
-    ba, bg = b[:inner].reshape(inner // hb, hb), b[inner:].reshape(inner // hb, hb)
-    wp = torch.cat([wa, wg], dim=1).reshape(2 * inner, -1)
-    bp = torch.cat([ba, bg], dim=1).reshape(2 * inner)
-    return _h(wp, dev), _f(bp, dev)
+    a = torch.arange(inner).reshape(inner // hb, hb)
+    return torch.cat([a, a + inner], dim=1).reshape(-1)
+
+
+def fold_layernorm(w: torch.Tensor, b: Optional[torch.Tensor], norm, dev, perm: Optional[torch.Tensor] = None):
+    """LN(x) @ W^T + b  ==  rstd * (x @ Wg^T - mean * u) + c  with Wg = W * gamma (fp16), u = rowsum(Wg) computed from
+    the ROUNDED fp16 weights (so the subtraction cancels exactly what the tensor core accumulated), c = W beta + b."""
+    w32 = w.detach().float().reshape(w.shape[0], -1)
+    wg16 = (w32 * norm.weight.detach().float()[None, :]).half()
+    u = wg16.float().sum(dim=1)
+    c = w32 @ norm.bias.detach().float()
+    if b is not None:
+        c = c + b.detach().float()
+    if perm is not None:
+        wg16, u, c = wg16[perm], u[perm], c[perm]
+    return _P(w=wg16.to(dev).contiguous(), u=_f(u, dev), c=_f(c, dev), eps=float(norm.eps))
 
 
 class _P:
@@ -75,20 +86,21 @@ def pack_norm(m, dev):
 
 
 def pack_transformer_block(tb, dev, cross: bool):
+    """LayerNorms are folded into the GEMM that consumes them (fold_layernorm); q/k/v projections fused."""
     inner = tb.attn1.to_q.weight.shape[0]
     p = _P(inner=inner)
-    p.n1, p.n2, p.n3 = pack_norm(tb.norm1, dev), pack_norm(tb.norm2, dev), pack_norm(tb.norm3, dev)
-    p.qkv1 = _h(torch.cat([tb.attn1.to_q.weight, tb.attn1.to_k.weight, tb.attn1.to_v.weight], 0), dev)
-    p.o1_w, p.o1_b = pack_linear(tb.attn1.to_out[0].weight, dev), _f(tb.attn1.to_out[0].bias, dev)
+    a1, a2 = tb.attn1, tb.attn2
+    p.qkv1 = fold_layernorm(torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], 0), None, tb.norm1, dev)
+    p.o1_w, p.o1_b = pack_linear(a1.to_out[0].weight, dev), _f(a1.to_out[0].bias, dev)
     if cross:
-        p.q2 = pack_linear(tb.attn2.to_q.weight, dev)
-        p.kv_txt = _h(torch.cat([tb.attn2.to_k.weight, tb.attn2.to_v.weight], 0), dev)
-        p.kv_img = (_h(torch.cat([tb.attn2.to_k_ip.weight, tb.attn2.to_v_ip.weight], 0), dev)
-                    if hasattr(tb.attn2, "to_k_ip") else None)
+        p.q2 = fold_layernorm(a2.to_q.weight, None, tb.norm2, dev)
+        p.kv_txt = _h(torch.cat([a2.to_k.weight, a2.to_v.weight], 0), dev)
+        p.kv_img = (_h(torch.cat([a2.to_k_ip.weight, a2.to_v_ip.weight], 0), dev) if hasattr(a2, "to_k_ip") else None)
     else:
-        p.qkv2 = _h(torch.cat([tb.attn2.to_q.weight, tb.attn2.to_k.weight, tb.attn2.to_v.weight], 0), dev)
-    p.o2_w, p.o2_b = pack_linear(tb.attn2.to_out[0].weight, dev), _f(tb.attn2.to_out[0].bias, dev)
-    p.ff1_w, p.ff1_b = pack_geglu(tb.ff.net[0].proj.weight.detach(), tb.ff.net[0].proj.bias.detach(), dev)
+        p.qkv2 = fold_layernorm(torch.cat([a2.to_q.weight, a2.to_k.weight, a2.to_v.weight], 0), None, tb.norm2, dev)
+    p.o2_w, p.o2_b = pack_linear(a2.to_out[0].weight, dev), _f(a2.to_out[0].bias, dev)
+    proj = tb.ff.net[0].proj
+    p.ff1 = fold_layernorm(proj.weight, proj.bias, tb.norm3, dev, perm=geglu_perm(proj.weight.shape[0]))
     p.ff2_w, p.ff2_b = pack_linear(tb.ff.net[2].weight, dev), _f(tb.ff.net[2].bias, dev)
     return p
 
@@ -96,7 +108,7 @@ def pack_transformer_block(tb, dev, cross: bool):
 # ------------------------------------------------------------------------------------------------ shared builders
 def gemm(bld: Builder, a: Act, w: torch.Tensor, taps, out: Act, *, a_dims=None, a_strides=None, out_dims=None,
          bias=None, bias2=None, bias2_rows_per=0, res: Optional[Act] = None, acc_scale=1.0, geglu=False,
-         n_cols=None, block_n=0):
+         n_cols=None, block_n=0, ln_stats=None, ln_u=None):
     """Record one tc_conv_gemm launch: out = epilogue(im2col(a) @ w.T)."""
     if a_dims is None:
         a_dims = (a.N, a.H, a.W, a.C)
@@ -107,7 +119,7 @@ def gemm(bld: Builder, a: Act, w: torch.Tensor, taps, out: Act, *, a_dims=None, 
     bld.op(ops.conv_gemm, a.t, a_dims, a_strides, w, taps, out.t, out_dims, n_cols, ldc=out.ld, bias=bias,
            bias2=bias2, bias2_rows_per=bias2_rows_per, res=None if res is None else res.t,
            ldr=None if res is None else res.ld, acc_scale=acc_scale, geglu=geglu, block_n=block_n, a_offset=a.off,
-           out_offset=out.off, res_offset=0 if res is None else res.off)
+           out_offset=out.off, res_offset=0 if res is None else res.off, ln_stats=ln_stats, ln_u=ln_u)
 
 
 def linear(bld: Builder, a: Act, w, out: Act, **kw):
@@ -129,18 +141,20 @@ def groupnorm(bld: Builder, x: Act, y: Act, n: _P, *, frames_per_stat=1, silu=Fa
            eps=n.eps if eps is None else eps, silu=silu, ldx=x.ld, ldy=y.ld, x_offset=x.off, y_offset=y.off)
 
 
-def layernorm(bld: Builder, x: Act, y: Act, n: _P):
-    assert x.off == 0 and y.off == 0
-    bld.op(ops.layernorm, x.t, y.t, n.g, n.b, rows=x.rows, C=x.C, eps=n.eps, ldx=x.ld, ldy=y.ld)
+def ln_linear(bld: Builder, x: Act, f: _P, out: Act, **kw):
+    """out = LN(x) @ W^T (+ ...) with the LayerNorm folded into the GEMM epilogue: one statistics pass over x
+    (tc_row_stats) replaces the LayerNorm kernel and its normalised fp16 copy of x."""
+    assert x.off == 0
+    stats, off = bld.raw(2 * x.rows, torch.float32)
+    bld.op(ops.row_stats, x.t, stats, rows=x.rows, C=x.C, eps=f.eps, ldx=x.ld)
+    linear(bld, x, f.w, out, bias=f.c, ln_stats=stats, ln_u=f.u, **kw)
+    bld.free_raw(off)
 
 
 def feed_forward(bld: Builder, x: Act, p: _P, out: Act):
     """x + W2 (a * gelu(g)), with (a, g) = W1 LN(x)   (attention.py:245, 415-442)."""
-    ln = bld.act(x.N, x.H, x.W, x.C)
-    layernorm(bld, x, ln, p.n3)
     hid = bld.act(x.N, x.H, x.W, 4 * x.C)
-    linear(bld, ln, p.ff1_w, hid, bias=p.ff1_b, geglu=True, block_n=GEGLU_BN)
-    ln.free()
+    ln_linear(bld, x, p.ff1, hid, geglu=True, block_n=GEGLU_BN)
     linear(bld, hid, p.ff2_w, out, bias=p.ff2_b, res=x)
     hid.free()
 
@@ -287,11 +301,8 @@ class UNetEngine:
         h2.free()
 
     def _self_attn_spatial(self, bld, x: Act, tb: _P, heads: int, out: Act):
-        ln = bld.act(x.N, x.H, x.W, x.C)
-        layernorm(bld, x, ln, tb.n1)
         qkv = bld.act(x.N, x.H, x.W, 3 * x.C)
-        linear(bld, ln, tb.qkv1, qkv)
-        ln.free()
+        ln_linear(bld, x, tb.qkv1, qkv)
         att = bld.act(x.N, x.H, x.W, x.C)
         L, C = x.H * x.W, x.C
         bld.op(ops.attention, qkv.t, [dict(k=qkv.t, v=qkv.t, ldk=3 * C, ldv=3 * C, Lk=L, k_offset=C, v_offset=2 * C)],
@@ -301,11 +312,8 @@ class UNetEngine:
         att.free()
 
     def _cross_attn(self, bld, x: Act, tb: _P, heads: int, out: Act, kv, st):
-        ln = bld.act(x.N, x.H, x.W, x.C)
-        layernorm(bld, x, ln, tb.n2)
         q = bld.act(x.N, x.H, x.W, x.C)
-        linear(bld, ln, tb.q2, q)
-        ln.free()
+        ln_linear(bld, x, tb.q2, q)
         att = bld.act(x.N, x.H, x.W, x.C)
         L, C, T = x.H * x.W, x.C, st["T"]
         segs = [dict(k=kv["txt"], v=kv["txt"], ldk=2 * C, ldv=2 * C, Lk=kv["n_txt"], kv_div=T, v_offset=C)]
@@ -335,12 +343,9 @@ class UNetEngine:
         linear(bld, t3, p.out_w, dst, bias=p.out_b, res=x)
         t3.free()
 
-    def _temporal_self_attn(self, bld, x: Act, norm: _P, wqkv, wo, bo, heads: int, out: Act, st):
-        ln = bld.act(x.N, x.H, x.W, x.C)
-        layernorm(bld, x, ln, norm)
+    def _temporal_self_attn(self, bld, x: Act, fqkv: _P, wo, bo, heads: int, out: Act, st):
         qkv = bld.act(x.N, x.H, x.W, 3 * x.C)
-        linear(bld, ln, wqkv, qkv)
-        ln.free()
+        ln_linear(bld, x, fqkv, qkv)
         att = bld.act(x.N, x.H, x.W, x.C)
         C = x.C
         bld.op(ops.temporal_attention, qkv.t, qkv.t, qkv.t, att.t, ld=3 * C, ldo=C, B=st["B"], T=st["T"], P=x.H * x.W,
@@ -358,10 +363,10 @@ class UNetEngine:
         n.free()
         tb = p.tb
         t1 = bld.act(N, H, W, p.inner)
-        self._temporal_self_attn(bld, t0, tb.n1, tb.qkv1, tb.o1_w, tb.o1_b, p.heads, t1, st)
+        self._temporal_self_attn(bld, t0, tb.qkv1, tb.o1_w, tb.o1_b, p.heads, t1, st)
         t0.free()
         t2 = bld.act(N, H, W, p.inner)
-        self._temporal_self_attn(bld, t1, tb.n2, tb.qkv2, tb.o2_w, tb.o2_b, p.heads, t2, st)
+        self._temporal_self_attn(bld, t1, tb.qkv2, tb.o2_w, tb.o2_b, p.heads, t2, st)
         t1.free()
         t3 = bld.act(N, H, W, p.inner)
         feed_forward(bld, t2, tb, t3)

@@ -54,7 +54,8 @@ def conv_gemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, taps: Sequenc
               out_dims, n_cols: int, *, ldc: Optional[int] = None, bias: Optional[torch.Tensor] = None,
               bias2: Optional[torch.Tensor] = None, bias2_rows_per: int = 0, res: Optional[torch.Tensor] = None,
               ldr: Optional[int] = None, acc_scale: float = 1.0, geglu: bool = False, block_n: int = 0,
-              a_offset: int = 0, out_offset: int = 0, res_offset: int = 0) -> None:
+              a_offset: int = 0, out_offset: int = 0, res_offset: int = 0,
+              ln_stats: Optional[torch.Tensor] = None, ln_u: Optional[torch.Tensor] = None) -> None:
     """out = epilogue(im2col(a) @ w.T).  a_dims = (N, H, W, C), a_strides = (sN, sH, sW) in elements.
 
     `*_offset` are element offsets applied to the base pointers (channel-slice views).
@@ -91,6 +92,9 @@ def conv_gemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, taps: Sequenc
     d.acc_scale = acc_scale
     d.flags = TC_EPI_GEGLU if geglu else 0
     d.block_n = block_n
+    if ln_stats is not None:
+        d.ln_stats = ln_stats.data_ptr()
+        d.ln_u = ln_u.data_ptr()
     check(lib.tc_conv_gemm(C.byref(d), _stream()), "tc_conv_gemm")
 
 
@@ -125,6 +129,15 @@ def groupnorm(x: torch.Tensor, y: torch.Tensor, gamma: torch.Tensor, beta: torch
                            y.data_ptr() + 2 * y_offset, ldy if ldy is not None else C,
                            gamma.data_ptr(), beta.data_ptr(), frames, frames_per_stat, hw, C, G, eps,
                            1 if silu else 0, ws.data_ptr(), _stream()), "tc_groupnorm")
+
+
+def row_stats(x: torch.Tensor, stats: torch.Tensor, *, rows: int, C: int, eps: float = 1e-5,
+              ldx: Optional[int] = None) -> None:
+    """stats[r] = (mean, rstd) of row r (LayerNorm statistics; the affine part is folded into the next GEMM)."""
+    _req_half(x, "x")
+    lib = _lib.load()
+    check(lib.tc_row_stats(x.data_ptr(), ldx if ldx is not None else C, rows, C, eps, stats.data_ptr(), _stream()),
+          "tc_row_stats")
 
 
 def layernorm(x: torch.Tensor, y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows: int, C: int,
