@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     uint64_t* tfull_bar = empty_bar + S;   // [2]
     uint64_t* tempty_bar = tfull_bar + 2;  // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    // epilogue staging of the per-column vectors (bias, folded-LayerNorm u): [2 accumulators][bias 256 | u 256] floats
+    float* s_epi = reinterpret_cast<float*>(tmem_ptr_smem + 4);
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&p.tmA);
@@ -274,8 +276,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 }
             }
 
+            // ---- per-column vectors of this N tile -> smem (global latency hidden behind the tile's mainloop; reading
+            // them with __ldg after the TMEM load put an L2 round trip on every 16-column chunk: profiles/r01_ncu_lin320)
+            float* sbias = s_epi + acc * 512;
+            float* su = sbias + 256;
+            {
+                const int e = (int)threadIdx.x - 64;            // 0..255 over the 8 epilogue warps
+                const int col = nt * BN + e;
+                const bool ok = e < BN && col < p.n_cols;
+                if (p.bias) sbias[e] = ok ? __ldg(p.bias + col) : 0.f;
+                if (p.ln_u) su[e] = ok ? __ldg(p.ln_u + col) : 0.f;
+            }
+
             tc::mbar_wait(&tfull_bar[acc], acc_phase);
             tc::tc_fence_after();
+            asm volatile("bar.sync 1, 256;" ::: "memory");       // staging visible to all epilogue warps
             const uint32_t taddr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(q * 32) << 16);
 
             if (!geglu) {
@@ -297,10 +312,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
                     if (vec_ok) {
                         if (p.ln_u) {
-                            const float* urow = p.ln_u + (long long)nt * BN + c;
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const float4 u4 = __ldg(reinterpret_cast<const float4*>(urow) + i);
+                                const float4 u4 = reinterpret_cast<const float4*>(su + c)[i];
                                 v[4 * i] = ln_rstd * (v[4 * i] - ln_mean * u4.x);
                                 v[4 * i + 1] = ln_rstd * (v[4 * i + 1] - ln_mean * u4.y);
                                 v[4 * i + 2] = ln_rstd * (v[4 * i + 2] - ln_mean * u4.z);
@@ -310,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                         if (brow) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c) + i);
+                                const float4 b4 = reinterpret_cast<const float4*>(sbias + c)[i];
                                 v[4 * i] += b4.x;
                                 v[4 * i + 1] += b4.y;
                                 v[4 * i + 2] += b4.z;
@@ -381,16 +395,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     for (int i = 0; i < 4; ++i) {
                         float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
                         if (brow) {
-                            ba = __ldg(reinterpret_cast<const float4*>(brow + c) + i);
-                            bg = __ldg(reinterpret_cast<const float4*>(brow + half_bn + c) + i);
+                            ba = reinterpret_cast<const float4*>(sbias + c)[i];
+                            bg = reinterpret_cast<const float4*>(sbias + half_bn + c)[i];
                         }
                         float a0 = __uint_as_float(ra[4 * i]), a1 = __uint_as_float(ra[4 * i + 1]);
                         float a2 = __uint_as_float(ra[4 * i + 2]), a3 = __uint_as_float(ra[4 * i + 3]);
                         float g0 = __uint_as_float(rg[4 * i]), g1 = __uint_as_float(rg[4 * i + 1]);
                         float g2 = __uint_as_float(rg[4 * i + 2]), g3 = __uint_as_float(rg[4 * i + 3]);
                         if (urow) {
-                            const float4 ua = __ldg(reinterpret_cast<const float4*>(urow + c) + i);
-                            const float4 ug = __ldg(reinterpret_cast<const float4*>(urow + half_bn + c) + i);
+                            const float4 ua = reinterpret_cast<const float4*>(su + c)[i];
+                            const float4 ug = reinterpret_cast<const float4*>(su + half_bn + c)[i];
                             a0 = ln_rstd * (a0 - ln_mean * ua.x);
                             a1 = ln_rstd * (a1 - ln_mean * ua.y);
                             a2 = ln_rstd * (a2 - ln_mean * ua.z);
@@ -545,12 +559,12 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
     }
 
     const int stage_bytes = kAStageBytes + (pair ? BN / 2 : BN) * 128;
-    const int smem_budget = 227 * 1024 - 1024 - 512;
+    const int smem_budget = 227 * 1024 - 1024 - 512 - 4096;   // alignment slack, barriers, epilogue staging
     int stages = smem_budget / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) return fail(TC_ERR_INVALID, "tc_conv_gemm: not enough shared memory for 2 stages");
     p.stages = stages;
-    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512 + 4096;
 
     static bool attr_set = false;
     if (!attr_set) {
