@@ -441,13 +441,41 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     }
 }
 
-int pick_block_n(int n_cols) {
+// Tile-shape heuristic: pick (block_n, single / CTA-pair) minimising   waves x per-tile cycles   with a small model
+// measured on B200: an M128 x N x K64 k-block costs max(2 N tensor cycles, ~200 issue cycles), plus ~1500 cycles of
+// per-tile pipeline fill / epilogue tail.  Matters for the 10x16 and 5x8 UNet levels (M = 5120 / 1280 rows), where
+// one wave of 256-wide tiles leaves most SMs idle.
+struct TileChoice {
+    int bn;
+    bool pair;
+};
+
+TileChoice choose_tiles(int tiles_m, int n_cols, int kblocks, int forced_bn, int sms) {
     const int n16 = (n_cols + 15) / 16 * 16;
-    if (n16 <= 256) return n16;
-    // largest multiple of 16 <= 256 that divides n16, but not smaller than 128
-    for (int bn = 256; bn >= 128; bn -= 16)
-        if (n16 % bn == 0) return bn;
-    return 256;
+    TileChoice best{n16 <= 256 ? n16 : 256, false};
+    double best_cost = 1e30;
+    for (int bn = 256; bn >= 16; bn -= 16) {
+        if (forced_bn > 0 && bn != forced_bn) continue;
+        if (forced_bn == 0) {
+            if (bn > n16) continue;
+            if (n16 > 256 ? (n16 % bn != 0 || bn < 64) : (bn != n16)) continue;   // whole tiles only
+        }
+        const int tiles_n = (n_cols + bn - 1) / bn;
+        const double kb_cost = (double)kblocks * (2.0 * bn > 200.0 ? 2.0 * bn : 200.0) + 1500.0 + 4.0 * bn;
+        for (int pair = 0; pair < 2; ++pair) {
+            if (pair && tiles_m < 2) continue;
+            const long long units = pair ? (long long)((tiles_m + 1) / 2) * tiles_n : (long long)tiles_m * tiles_n;
+            const int slots = pair ? sms / 2 : sms;
+            const long long waves = (units + slots - 1) / slots;
+            // the pair shares B between two SMs: ~10 % faster per tile when tensor-bound (measured), never slower
+            const double cost = (double)waves * kb_cost * (pair && 2.0 * bn > 200.0 ? 0.9 : 1.0);
+            if (cost < best_cost) {
+                best_cost = cost;
+                best = TileChoice{bn, pair != 0};
+            }
+        }
+    }
+    return best;
 }
 
 }  // namespace
@@ -470,10 +498,11 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
     TC_CHECK_ARG(!d->res || (d->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(d->res) & 15) == 0),
                  "tc_conv_gemm: residual must be 16-byte aligned");
     const bool geglu = (d->flags & TC_EPI_GEGLU) != 0;
-    int BN = d->block_n > 0 ? d->block_n : pick_block_n(d->n_cols);
-    TC_CHECK_ARG(BN % 16 == 0 && BN >= 16 && BN <= 256, "tc_conv_gemm: block_n must be a multiple of 16 in [16,256]");
+    int BN = d->block_n > 0 ? d->block_n : 0;   // 0: chosen below, once the M tiling is known
+    TC_CHECK_ARG(BN == 0 || (BN % 16 == 0 && BN >= 16 && BN <= 256),
+                 "tc_conv_gemm: block_n must be a multiple of 16 in [16,256]");
     if (geglu) {
-        TC_CHECK_ARG(BN % 32 == 0 && d->n_cols % BN == 0, "tc_conv_gemm: GEGLU needs n_cols % block_n == 0");
+        TC_CHECK_ARG(BN > 0 && BN % 32 == 0 && d->n_cols % BN == 0, "tc_conv_gemm: GEGLU needs n_cols % block_n == 0");
         TC_CHECK_ARG(!d->res && !d->bias2, "tc_conv_gemm: GEGLU epilogue takes bias only");
     }
 
@@ -511,6 +540,11 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
     p.tiles_y = (d->oH + p.TH - 1) / p.TH;
     p.tiles_n = (d->oN + p.TN - 1) / p.TN;
     p.tiles_m = p.tiles_x * p.tiles_y * p.tiles_n;
+    static const char* pair_env = getenv("TC_GEMM_PAIR");       // "0" / "1" force (A/B testing), unset = heuristic
+    TileChoice choice = choose_tiles(p.tiles_m, d->n_cols, d->taps * (d->a_C / kBlockK), BN, sm_count());
+    BN = choice.bn;
+    bool pair = choice.pair;
+    if (pair_env) pair = (pair_env[0] == '1') && p.tiles_m >= 2;
     p.BN = BN;
     p.tiles_nn = (d->n_cols + BN - 1) / BN;
     p.n_cols = d->n_cols;
@@ -544,11 +578,7 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
         if (!m) return TC_ERR_CUDA;
         p.tmA = *m;
     }
-    // CTA-pair mode when there is enough work to give every SM pair at least one tile pair
-    static const char* pair_env = getenv("TC_GEMM_PAIR");       // "0" / "1" force (A/B testing), unset = heuristic
     const long long pair_tiles = (long long)((p.tiles_m + 1) / 2) * p.tiles_nn;
-    bool pair = p.tiles_m >= 2 && pair_tiles >= sm_count() / 2;
-    if (pair_env) pair = (pair_env[0] == '1') && p.tiles_m >= 2;
     {
         uint64_t dims[2] = {(uint64_t)d->taps * (uint64_t)d->a_C, (uint64_t)d->b_rows};
         uint64_t strides[1] = {(uint64_t)d->ldb * 2};
