@@ -91,6 +91,8 @@ typedef struct {
 } TcConvGemm;
 
 int tc_conv_gemm(const TcConvGemm* desc, void* stream);
+/* profiling aid: 0 = normal, 1 = epilogue skips global stores, 2 = epilogue body skipped (results are then garbage) */
+int tc_debug_set_gemm_mode(int mode);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (+ optional SiLU), fp32 statistics, channels-last fp16 in/out.

@@ -54,7 +54,10 @@ struct alignas(64) GemmKParams {
     const float* ln_u;       // per column sum_k Wt[j][k]
 };
 
+__device__ int g_tc_gemm_debug = 0;   // profiling aid (scripts/prof_epilogue.py): 1 = no global stores, 2 = no epilogue body
+
 __device__ __forceinline__ void store_row16(__half* dst, const float (&v)[16], int ncols_valid) {
+    if (g_tc_gemm_debug & 1) return;
     if (ncols_valid >= 16) {
         uint4 u0, u1;
         __half2 h[8];
@@ -293,7 +296,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             asm volatile("bar.sync 1, 256;" ::: "memory");       // staging visible to all epilogue warps
             const uint32_t taddr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(q * 32) << 16);
 
-            if (!geglu) {
+            if (g_tc_gemm_debug & 2) {
+                // (profiling) accumulator is dropped: measures mainloop + handshake only
+            } else if (!geglu) {
                 __half* orow = p.out + m * p.ldc + (long long)nt * BN;
                 const __half* b2row =
                     p.bias2 ? p.bias2 + (row_ok ? (m / p.bias2_rows_per) : 0) * p.bias2_ld + (long long)nt * BN : nullptr;
@@ -479,6 +484,10 @@ TileChoice choose_tiles(int tiles_m, int n_cols, int kblocks, int forced_bn, int
 }
 
 }  // namespace
+
+extern "C" int tc_debug_set_gemm_mode(int mode) {
+    return tc_host::check_cuda(cudaMemcpyToSymbol(g_tc_gemm_debug, &mode, sizeof(int)), "tc_debug_set_gemm_mode");
+}
 
 extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
     using namespace tc_host;
