@@ -14,6 +14,8 @@
 // Roofline: tensor-bound (fp16 dense); algorithmic flops = 2 * M * n_cols * taps * C.
 #include <stdlib.h>
 
+#include <vector>
+
 #include "tc_common.cuh"
 #include "tc_host.h"
 
@@ -29,6 +31,9 @@ constexpr int kAccStride = 256;  // TMEM column offset of the second accumulator
 struct alignas(64) GemmKParams {
     CUtensorMap tmA;
     CUtensorMap tmB;
+    CUtensorMap tmR;   // residual viewed as an A operand (res_kblocks > 0)
+    CUtensorMap tmE;   // 256 x 256 identity (its B operand)
+    int res_kblocks;   // 0: residual (if any) is added in the epilogue from registers
     int taps;
     int tap_dx[TC_MAX_TAPS], tap_dy[TC_MAX_TAPS], tap_dn[TC_MAX_TAPS];
     int kc_per_tap;
@@ -109,6 +114,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&p.tmA);
         tc::tma_prefetch_desc(&p.tmB);
+        if (p.res_kblocks) {
+            tc::tma_prefetch_desc(&p.tmR);
+            tc::tma_prefetch_desc(&p.tmE);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < S; ++s) {
@@ -140,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     const int n_units = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int tiles_mu = kPair ? ((p.tiles_m + 1) >> 1) : p.tiles_m;
     const int total_tiles = tiles_mu * p.tiles_nn;
-    const int kblocks = p.taps * p.kc_per_tap;
+    const int kblocks = p.taps * p.kc_per_tap + p.res_kblocks;   // consumer view (residual k-blocks included)
     // tile -> (nt, mt) for this CTA; mt >= tiles_m (odd tail of a pair) decodes to out-of-range coordinates:
     // its TMA boxes are zero-filled and its rows are never stored
 #define TC_DECODE_TILE(tile)                                                   \
@@ -185,6 +194,29 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                             stage = 0;
                             phase ^= 1u;
                         }
+                    }
+                }
+                // residual as extra k-blocks: out += R[tile rows][tile cols] @ I  (TMA-coalesced, fully async; loading it
+                // from registers in the epilogue cost 32 us of a 81 us launch at M=81920, N=K=320: prof_epilogue.py)
+                for (int r = 0; r < p.res_kblocks; ++r) {
+                    tc::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    if (tc::elect_one()) {
+                        uint8_t* dA = sA + (size_t)stage * kAStageBytes;
+                        uint8_t* dB = sB + (size_t)stage * b_stage_bytes;
+                        if constexpr (kPair) {
+                            if (rank == 0) tc::mbar_arrive_expect_tx(&full_bar[stage], 2u * (p.a_bytes + b_stage_bytes));
+                            tc::tma_load_4d_pair(dA, &p.tmR, &full_bar[stage], nt * BN + r * kBlockK, x0, y0, n0);
+                            tc::tma_load_2d_pair(dB, &p.tmE, &full_bar[stage], r * kBlockK, (int)rank * b_rows);
+                        } else {
+                            tc::mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + b_stage_bytes);
+                            tc::tma_load_4d(dA, &p.tmR, &full_bar[stage], nt * BN + r * kBlockK, x0, y0, n0);
+                            tc::tma_load_2d(dB, &p.tmE, &full_bar[stage], r * kBlockK, 0);
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1u;
                     }
                 }
             }
@@ -261,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             const int x = tx * p.TW + rx, y = ty * p.TH + ry, n = tn * p.TN + rn;
             const bool row_ok = (rn < p.TN) && (x < p.oW) && (y < p.oH) && (n < p.oN);
             const long long m = ((long long)n * p.oH + y) * p.oW + x;
-            const __half* rrow = (p.res && row_ok) ? p.res + m * p.ldr + (long long)nt * BN : nullptr;
+            const __half* rrow = (p.res && p.res_kblocks == 0 && row_ok) ? p.res + m * p.ldr + (long long)nt * BN : nullptr;
 
             float ln_mean = 0.f, ln_rstd = 1.f;
             if (p.ln_stats && row_ok) {
@@ -446,6 +478,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     }
 }
 
+// 256 x 256 fp16 identity used as the B operand of the residual k-blocks (lazily created once per process; the only
+// device allocation this library ever makes)
+const __half* identity_table() {
+    static __half* dev = nullptr;
+    if (!dev) {
+        std::vector<__half> h(256 * 256, __float2half(0.f));
+        for (int i = 0; i < 256; ++i) h[i * 256 + i] = __float2half(1.f);
+        if (cudaMalloc(&dev, h.size() * sizeof(__half)) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(dev, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    }
+    return dev;
+}
+
 // Tile-shape heuristic: pick (block_n, single / CTA-pair) minimising   waves x per-tile cycles   with a small model
 // measured on B200: an M128 x N x K64 k-block costs max(2 N tensor cycles, ~200 issue cycles), plus ~1500 cycles of
 // per-tile pipeline fill / epilogue tail.  Matters for the 10x16 and 5x8 UNet levels (M = 5120 / 1280 rows), where
@@ -597,6 +642,27 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
         p.tmB = *m;
     }
 
+    // residual through the tensor core when the K loop is short (epilogue-bound regime) and no scaling is involved
+    const int main_kblocks = d->taps * (d->a_C / kBlockK);
+    static const char* resmma_env = getenv("TC_GEMM_RES_MMA");   // "0" disables (A/B testing)
+    if (d->res && !geglu && d->acc_scale == 1.0f && main_kblocks <= 24 && d->n_cols % 8 == 0 &&
+        !(resmma_env && resmma_env[0] == '0')) {
+        const __half* eye = identity_table();
+        if (!eye) return fail(TC_ERR_CUDA, "tc_conv_gemm: identity table allocation failed");
+        p.res_kblocks = (BN + kBlockK - 1) / kBlockK;
+        uint64_t rdims[4] = {(uint64_t)d->n_cols, (uint64_t)d->oW, (uint64_t)d->oH, (uint64_t)d->oN};
+        uint64_t rstr[3] = {(uint64_t)d->ldr * 2, (uint64_t)d->oW * (uint64_t)d->ldr * 2,
+                            (uint64_t)d->oH * (uint64_t)d->oW * (uint64_t)d->ldr * 2};
+        uint32_t rbox[4] = {(uint32_t)kBlockK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+        const CUtensorMap* mr = get_tensor_map(d->res, 4, rdims, rstr, rbox);
+        uint64_t edims[2] = {256, 256};
+        uint64_t estr[1] = {256 * 2};
+        uint32_t ebox[2] = {(uint32_t)kBlockK, (uint32_t)(pair ? BN / 2 : BN)};
+        const CUtensorMap* me = get_tensor_map(eye, 2, edims, estr, ebox);
+        if (!mr || !me) return TC_ERR_CUDA;
+        p.tmR = *mr;
+        p.tmE = *me;
+    }
     const int stage_bytes = kAStageBytes + (pair ? BN / 2 : BN) * 128;
     const int smem_budget = 227 * 1024 - 1024 - 512 - 4096;   // alignment slack, barriers, epilogue staging
     int stages = smem_budget / stage_bytes;
