@@ -159,6 +159,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// ---- TMA stores (shared -> global, bulk async group completion) ---------------------------------------
+__device__ __forceinline__ void tma_store_4d(const void* smem_src, const void* tmap, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        :
+        : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest kN groups have finished READING their shared-memory source (buffer reusable)
+template <int kN>
+__device__ __forceinline__ void bulk_wait_group_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kN) : "memory");
+}
+template <int kN>
+__device__ __forceinline__ void bulk_wait_group() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kN) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 

@@ -34,6 +34,8 @@ struct alignas(64) GemmKParams {
     CUtensorMap tmR;   // residual viewed as an A operand (res_kblocks > 0)
     CUtensorMap tmE;   // 256 x 256 identity (its B operand)
     int res_kblocks;   // 0: residual (if any) is added in the epilogue from registers
+    CUtensorMap tmO;   // output, box {32 cols, TW, TH, TN}, 64B swizzle (tma_store != 0)
+    int tma_store;     // epilogue writes through shared memory + TMA stores (whole 32-column chunks)
     int taps;
     int tap_dx[TC_MAX_TAPS], tap_dy[TC_MAX_TAPS], tap_dn[TC_MAX_TAPS];
     int kc_per_tap;
@@ -110,6 +112,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     // epilogue staging of the per-column vectors (bias, folded-LayerNorm u): [2 accumulators][bias 256 | u 256] floats
     float* s_epi = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+    // output staging for the TMA-store epilogue: one 128-row x 32-column (64 B, 64B-swizzled) box per column group
+    uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_epi + 1024) + 1023) & ~uintptr_t(1023));
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&p.tmA);
@@ -118,6 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             tc::tma_prefetch_desc(&p.tmR);
             tc::tma_prefetch_desc(&p.tmE);
         }
+        if (p.tma_store) tc::tma_prefetch_desc(&p.tmO);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < S; ++s) {
@@ -286,6 +291,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         const int c_begin = cg == 0 ? 0 : split;
         const int c_end = cg == 0 ? split : width;
         const bool vec_ok = (p.n_cols % 16) == 0;                   // all chunks complete -> 16-byte paths
+        // TMA-store path: 32-column chunks, chunk k belongs to column group k & 1
+        const bool tma_out = p.tma_store != 0;
+        uint8_t* stg = s_stage + cg * 8192;
+        const bool store_leader = (warp == 2 + 4 * cg) && lane == 0;
+        const uint32_t stg_row = tc::smem_u32(stg) + (uint32_t)row * 64u;
+        const uint32_t stg_swz = (uint32_t)((row >> 1) & 3);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = unit; tile < total_tiles; tile += n_units) {
@@ -303,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             }
             // ---- residual prefetch (up to 128 columns = 16 x 16 B per thread)
             uint4 rres[16];
-            if (rrow && vec_ok) {
+            if (rrow && vec_ok && !tma_out) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int c = c_begin + j * 8;
@@ -330,6 +341,141 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 
             if (g_tc_gemm_debug & 2) {
                 // (profiling) accumulator is dropped: measures mainloop + handshake only
+            } else if (tma_out) {
+                // ---- TMEM -> registers -> swizzled smem box -> one TMA store per 128 x 32 chunk.  Per-thread 16-byte
+                // global stores touch 32 different lines per instruction (LSU: 16 B/clk instead of 128 B/clk) and cost
+                // 30-35 % of the K = 320 launches (scripts/prof_epilogue.py, mode 0 vs 1).
+                const int half_bn = BN >> 1;
+                const __half* b2row =
+                    p.bias2 ? p.bias2 + (row_ok ? (m / p.bias2_rows_per) : 0) * p.bias2_ld + (long long)nt * BN : nullptr;
+                const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+#pragma unroll 1
+                for (int jc = 0; jc < 4; ++jc) {
+                    const int c = (cg + 2 * jc) * 32;
+                    if (c >= width) break;
+                    float v[32];
+                    if (!geglu) {
+                        // register-path residual (long K loops / scaled accumulators only: the epilogue has slack there)
+                        uint4 rr[4];
+                        if (rrow) {
+#pragma unroll
+                            for (int hh = 0; hh < 4; ++hh) rr[hh] = *reinterpret_cast<const uint4*>(rrow + c + hh * 8);
+                        }
+                        uint32_t r[32];
+                        tc::tmem_ld32(taddr + (uint32_t)c, r);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                        if (p.ln_u) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 u4 = reinterpret_cast<const float4*>(su + c)[i];
+                                v[4 * i] = ln_rstd * (v[4 * i] - ln_mean * u4.x);
+                                v[4 * i + 1] = ln_rstd * (v[4 * i + 1] - ln_mean * u4.y);
+                                v[4 * i + 2] = ln_rstd * (v[4 * i + 2] - ln_mean * u4.z);
+                                v[4 * i + 3] = ln_rstd * (v[4 * i + 3] - ln_mean * u4.w);
+                            }
+                        }
+                        if (p.bias) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 b4 = reinterpret_cast<const float4*>(sbias + c)[i];
+                                v[4 * i] += b4.x;
+                                v[4 * i + 1] += b4.y;
+                                v[4 * i + 2] += b4.z;
+                                v[4 * i + 3] += b4.w;
+                            }
+                        }
+                        if (b2row) {
+#pragma unroll
+                            for (int hh = 0; hh < 4; ++hh) {
+                                const uint4 u = __ldg(reinterpret_cast<const uint4*>(b2row + c) + hh);
+                                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float2 f = __half22float2(h2[i]);
+                                    v[hh * 8 + 2 * i] += f.x;
+                                    v[hh * 8 + 2 * i + 1] += f.y;
+                                }
+                            }
+                        }
+                        if (p.acc_scale != 1.0f) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] *= p.acc_scale;
+                        }
+                        if (rrow) {
+#pragma unroll
+                            for (int hh = 0; hh < 4; ++hh) {
+                                const uint4 u = rr[hh];
+                                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float2 f = __half22float2(h2[i]);
+                                    v[hh * 8 + 2 * i] += f.x;
+                                    v[hh * 8 + 2 * i + 1] += f.y;
+                                }
+                            }
+                        }
+                    } else {
+                        // weight rows of this N tile are [value half (BN/2) | gate half (BN/2)]
+#pragma unroll
+                        for (int h16 = 0; h16 < 2; ++h16) {
+                            uint32_t ra[16], rg[16];
+                            const int cc = c + h16 * 16;
+                            tc::tmem_ld16(taddr + (uint32_t)cc, ra);
+                            tc::tmem_ld16(taddr + (uint32_t)(half_bn + cc), rg);
+                            tc::tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+                                if (p.bias) {
+                                    ba = reinterpret_cast<const float4*>(sbias + cc)[i];
+                                    bg = reinterpret_cast<const float4*>(sbias + half_bn + cc)[i];
+                                }
+                                float a0 = __uint_as_float(ra[4 * i]), a1 = __uint_as_float(ra[4 * i + 1]);
+                                float a2 = __uint_as_float(ra[4 * i + 2]), a3 = __uint_as_float(ra[4 * i + 3]);
+                                float g0 = __uint_as_float(rg[4 * i]), g1 = __uint_as_float(rg[4 * i + 1]);
+                                float g2 = __uint_as_float(rg[4 * i + 2]), g3 = __uint_as_float(rg[4 * i + 3]);
+                                if (p.ln_u) {
+                                    const float4 ua = reinterpret_cast<const float4*>(su + cc)[i];
+                                    const float4 ug = reinterpret_cast<const float4*>(su + half_bn + cc)[i];
+                                    a0 = ln_rstd * (a0 - ln_mean * ua.x);
+                                    a1 = ln_rstd * (a1 - ln_mean * ua.y);
+                                    a2 = ln_rstd * (a2 - ln_mean * ua.z);
+                                    a3 = ln_rstd * (a3 - ln_mean * ua.w);
+                                    g0 = ln_rstd * (g0 - ln_mean * ug.x);
+                                    g1 = ln_rstd * (g1 - ln_mean * ug.y);
+                                    g2 = ln_rstd * (g2 - ln_mean * ug.z);
+                                    g3 = ln_rstd * (g3 - ln_mean * ug.w);
+                                }
+                                v[h16 * 16 + 4 * i] = (a0 + ba.x) * tc::gelu_erf_f(g0 + bg.x);
+                                v[h16 * 16 + 4 * i + 1] = (a1 + ba.y) * tc::gelu_erf_f(g1 + bg.y);
+                                v[h16 * 16 + 4 * i + 2] = (a2 + ba.z) * tc::gelu_erf_f(g2 + bg.z);
+                                v[h16 * 16 + 4 * i + 3] = (a3 + ba.w) * tc::gelu_erf_f(g3 + bg.w);
+                            }
+                        }
+                    }
+                    // the previous chunk's TMA store must have drained the staging box before it is overwritten
+                    if (store_leader) tc::bulk_wait_group_read<0>();
+                    if (cg == 0) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
+#pragma unroll
+                    for (int hh = 0; hh < 4; ++hh) {
+                        __half2 h[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[hh * 8 + 2 * i], v[hh * 8 + 2 * i + 1]);
+                        const uint32_t dst = stg_row + ((((uint32_t)hh) ^ stg_swz) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                                     "r"(*reinterpret_cast<uint32_t*>(&h[0])), "r"(*reinterpret_cast<uint32_t*>(&h[1])),
+                                     "r"(*reinterpret_cast<uint32_t*>(&h[2])), "r"(*reinterpret_cast<uint32_t*>(&h[3]))
+                                     : "memory");
+                    }
+                    tc::fence_proxy_async_smem();
+                    if (cg == 0) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
+                    if (store_leader && !(g_tc_gemm_debug & 1)) {
+                        tc::tma_store_4d(stg, &p.tmO, nt * width + c, x0, y0, n0);
+                        tc::bulk_commit_group();
+                    }
+                }
             } else if (!geglu) {
                 __half* orow = p.out + m * p.ldc + (long long)nt * BN;
                 const __half* b2row =
@@ -470,6 +616,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     }
 #undef TC_DECODE_TILE
 
+    if (p.tma_store && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) tc::bulk_wait_group<0>();
     tc::tc_fence_before();
     if constexpr (kPair) tc::cluster_sync_all(); else __syncthreads();   // the peer may still read our smem / barriers
     if (warp == 2) {
@@ -508,7 +655,8 @@ TileChoice choose_tiles(int tiles_m, int n_cols, int kblocks, int forced_bn, int
         if (forced_bn > 0 && bn != forced_bn) continue;
         if (forced_bn == 0) {
             if (bn > n16) continue;
-            if (n16 > 256 ? (n16 % bn != 0 || bn < 64) : (bn != n16)) continue;   // whole tiles only
+            // whole tiles only; 32-column granularity keeps the TMA-store epilogue applicable
+            if (n16 > 256 ? (n16 % bn != 0 || bn < 64 || bn % 32 != 0) : (bn != n16)) continue;
         }
         const int tiles_n = (n_cols + bn - 1) / bn;
         const double kb_cost = (double)kblocks * (2.0 * bn > 200.0 ? 2.0 * bn : 200.0) + 1500.0 + 4.0 * bn;
@@ -663,13 +811,30 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
         p.tmR = *mr;
         p.tmE = *me;
     }
+    // TMA-store epilogue: whole 32-column chunks of 16-byte-aligned rows
+    {
+        const int width = geglu ? BN / 2 : BN;
+        const int out_cols = geglu ? d->n_cols / 2 : d->n_cols;
+        static const char* tmast_env = getenv("TC_GEMM_TMA_STORE");   // "0" disables (A/B testing)
+        if (d->n_cols % 16 == 0 && width % 32 == 0 && out_cols % width == 0 && !(tmast_env && tmast_env[0] == '0')) {
+            uint64_t odims[4] = {(uint64_t)out_cols, (uint64_t)d->oW, (uint64_t)d->oH, (uint64_t)d->oN};
+            uint64_t ostr[3] = {(uint64_t)d->ldc * 2, (uint64_t)d->oW * (uint64_t)d->ldc * 2,
+                                (uint64_t)d->oH * (uint64_t)d->oW * (uint64_t)d->ldc * 2};
+            uint32_t obox[4] = {32u, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+            const CUtensorMap* mo = get_tensor_map(d->out, 4, odims, ostr, obox, 64);
+            if (!mo) return TC_ERR_CUDA;
+            p.tmO = *mo;
+            p.tma_store = 1;
+        }
+    }
     const int stage_bytes = kAStageBytes + (pair ? BN / 2 : BN) * 128;
-    const int smem_budget = 227 * 1024 - 1024 - 512 - 4096;   // alignment slack, barriers, epilogue staging
+    const int kFixedSmem = 1024 + 512 + 4096 + 1024 + 16384;   // alignment slack, barriers, epilogue vectors, store staging
+    const int smem_budget = 227 * 1024 - kFixedSmem;
     int stages = smem_budget / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) return fail(TC_ERR_INVALID, "tc_conv_gemm: not enough shared memory for 2 stages");
     p.stages = stages;
-    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512 + 4096;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + kFixedSmem;
 
     static bool attr_set = false;
     if (!attr_set) {

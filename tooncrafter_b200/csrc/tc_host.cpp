@@ -55,13 +55,13 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 struct MapKey {
-    uint64_t v[14];
+    uint64_t v[15];
     bool operator==(const MapKey& o) const { return std::memcmp(v, o.v, sizeof(v)) == 0; }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey& k) const {
         uint64_t h = 1469598103934665603ull;
-        for (int i = 0; i < 14; ++i) {
+        for (int i = 0; i < 15; ++i) {
             h ^= k.v[i];
             h *= 1099511628211ull;
         }
@@ -74,7 +74,7 @@ static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap*, MapKeyHash> g_maps;
 
 const CUtensorMap* get_tensor_map(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                                  const uint32_t* box) {
+                                  const uint32_t* box, int swizzle_bytes) {
     MapKey key;
     std::memset(&key, 0, sizeof(key));
     key.v[0] = reinterpret_cast<uint64_t>(base);
@@ -82,6 +82,7 @@ const CUtensorMap* get_tensor_map(const void* base, int rank, const uint64_t* di
     for (int i = 0; i < rank; ++i) key.v[2 + i] = dims[i];
     for (int i = 0; i + 1 < rank; ++i) key.v[6 + i] = strides_bytes[i];
     for (int i = 0; i < rank; ++i) key.v[10 + i] = box[i];
+    key.v[14] = (uint64_t)swizzle_bytes;
 
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = g_maps.find(key);
@@ -109,7 +110,9 @@ const CUtensorMap* get_tensor_map(const void* base, int rank, const uint64_t* di
     }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
-                     es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[256];

@@ -309,7 +309,8 @@ extern "C" int tc_groupnorm(const void* x, long long ldx, void* y, long long ldy
     // each thread should see >= 8 pixels in the statistics pass; cap partial blocks per stat group
     long long want = (pps + (long long)k * 16 - 1) / ((long long)k * 16);
     int nblk = (int)(want < 1 ? 1 : want);
-    int cap = (2 * sm_count() + n_stat - 1) / n_stat;
+    // exactly one resident wave (2 blocks of <= 512 threads per SM): 320 blocks on 296 slots ran as two waves
+    int cap = (2 * sm_count()) / n_stat;
     if (cap < 1) cap = 1;
     if (cap > kGnMaxPartials) cap = kGnMaxPartials;
     if (nblk > cap) nblk = cap;
@@ -319,7 +320,9 @@ extern "C" int tc_groupnorm(const void* x, long long ldx, void* y, long long ldy
     TC_CHECK_LAUNCH("gn_stats_kernel");
     long long want2 = (pps + (long long)k * 8 - 1) / ((long long)k * 8);
     int nblk2 = (int)(want2 < 1 ? 1 : want2);
-    int cap2 = (8 * sm_count() + n_stat - 1) / n_stat;
+    // one wave as well: every block pays the fp64 finalize prologue once
+    int cap2 = (2 * sm_count()) / n_stat;
+    if (cap2 < 1) cap2 = 1;
     if (nblk2 > cap2) nblk2 = cap2;
     gn_apply_kernel<<<dim3(nblk2, n_stat), threads, 2 * G * sizeof(float), stream>>>(
         reinterpret_cast<const __half*>(x), ldx, reinterpret_cast<__half*>(y), ldy, gamma, beta, pps, C, G, eps, silu,
