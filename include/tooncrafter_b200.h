@@ -91,8 +91,10 @@ typedef struct {
 } TcConvGemm;
 
 int tc_conv_gemm(const TcConvGemm* desc, void* stream);
-/* profiling aid: 0 = normal, 1 = epilogue skips global stores, 2 = epilogue body skipped (results are then garbage) */
+/* profiling aids: mode bits 1 = epilogue skips global stores, 2 = epilogue body skipped (results are then garbage),
+ * 4 = record clock64() stamps per CTA / tile / warp role: [160 CTAs][32 tiles][16 slots] read back with *_read_gemm_trace */
 int tc_debug_set_gemm_mode(int mode);
+int tc_debug_read_gemm_trace(unsigned long long* host_dst, int count);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (+ optional SiLU), fp32 statistics, channels-last fp16 in/out.

@@ -63,6 +63,23 @@ def test_linear_bias_residual(ops, rows, K, N):
     assert (out[:, N:] == 0).all()
 
 
+@pytest.mark.parametrize("K,N,res", [(320, 320, True), (320, 960, False), (640, 640, True)])
+def test_linear_skinny_weight_resident(ops, K, N, res):
+    """M >> N with a short K loop: enough M tiles per SM that tc_conv_gemm keeps the weight N-tile resident in shared
+    memory (reloaded only when the N tile changes) and adds the residual through the tensor core."""
+    rows = 81920 if K == 320 else 61440
+    x = _rand(rows, K, seed=71).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=72).half()
+    bias = _rand(N, seed=73).float()
+    r = _rand(rows, N, seed=74).half() if res else None
+    out = torch.zeros(rows, N, dtype=torch.float16, device=DEV)
+    ops.linear(x, w, out, rows=rows, K=K, n_cols=N, bias=bias, res=r)
+    ref = x.float() @ w.float().t() + bias
+    if res:
+        ref = ref + r.float()
+    _close(out, ref, f"skinny linear {rows}x{K}x{N}")
+
+
 def test_linear_strided_slices(ops):
     """A read from / output written into channel slices of wider tensors (concat-by-construction)."""
     rows, K, N = 640, 128, 192

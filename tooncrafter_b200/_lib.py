@@ -63,6 +63,7 @@ _PROTOTYPES = {
     "tc_sm_count": (C.c_int, []),
     "tc_conv_gemm": (C.c_int, [C.POINTER(TcConvGemm), C.c_void_p]),
     "tc_debug_set_gemm_mode": (C.c_int, [C.c_int]),
+    "tc_debug_read_gemm_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "tc_groupnorm": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p,
                                C.c_void_p]),

@@ -14,8 +14,6 @@
 // Roofline: tensor-bound (fp16 dense); algorithmic flops = 2 * M * n_cols * taps * C.
 #include <stdlib.h>
 
-#include <vector>
-
 #include "tc_common.cuh"
 #include "tc_host.h"
 
@@ -32,10 +30,12 @@ struct alignas(64) GemmKParams {
     CUtensorMap tmA;
     CUtensorMap tmB;
     CUtensorMap tmR;   // residual viewed as an A operand (res_kblocks > 0)
-    CUtensorMap tmE;   // 256 x 256 identity (its B operand)
     int res_kblocks;   // 0: residual (if any) is added in the epilogue from registers
     CUtensorMap tmO;   // output, box {32 cols, TW, TH, TN}, 64B swizzle (tma_store != 0)
     int tma_store;     // epilogue writes through shared memory + TMA stores (whole 32-column chunks)
+    CUtensorMap tmOw;  // output, per-warp box {32 cols, wbW, wbH, wbN} (warp_box != 0)
+    int warp_box;      // each epilogue warp's 32 rows form a box: per-warp TMA stores, no 128-thread barriers
+    int b_resident;    // the whole K extent of one B (weight) N-tile stays in shared memory across M tiles
     int taps;
     int tap_dx[TC_MAX_TAPS], tap_dy[TC_MAX_TAPS], tap_dn[TC_MAX_TAPS];
     int kc_per_tap;
@@ -61,7 +61,13 @@ struct alignas(64) GemmKParams {
     const float* ln_u;       // per column sum_k Wt[j][k]
 };
 
-__device__ int g_tc_gemm_debug = 0;   // profiling aid (scripts/prof_epilogue.py): 1 = no global stores, 2 = no epilogue body
+__device__ int g_tc_gemm_debug = 0;   // profiling aid (scripts/prof_epilogue.py): 1 = no global stores, 2 = no epilogue body,
+                                      // 4 = record per-tile clock64() stamps of each warp role (scripts/trace_gemm.py)
+constexpr int kTraceTiles = 32, kTraceSlots = 16, kTraceCtas = 160;
+__device__ unsigned long long g_tc_gemm_trace[kTraceCtas * kTraceTiles * kTraceSlots];
+#define TC_TRACE(slot, ti)                                                                                   \
+    if ((g_tc_gemm_debug & 4) && (ti) < kTraceTiles && blockIdx.x < kTraceCtas)                                \
+        g_tc_gemm_trace[((int)blockIdx.x * kTraceTiles + (ti)) * kTraceSlots + (slot)] = (unsigned long long)clock64();
 
 __device__ __forceinline__ void store_row16(__half* dst, const float (&v)[16], int ncols_valid) {
     if (g_tc_gemm_debug & 1) return;
@@ -90,7 +96,9 @@ __device__ __forceinline__ void store_row16(__half* dst, const float (&v)[16], i
 // kPair = true: two CTAs of a cluster form one tcgen05 cta_group::2 pair (M = 256 per MMA, each CTA loads its own 128
 // A rows and HALF of the B tile), which cuts the shared-memory/L2 operand traffic per MAC by ~30-45 % — the single-CTA
 // kernel saturates at ~62 B/clk/SM of TMA ingest (profiles/r01_*conv320*).
-template <bool kPair>
+// kEpi: 0 = TMA-store epilogue, 1 = TMA-store GEGLU epilogue, 2 = legacy epilogue (direct 16-byte / scalar stores for
+// odd widths); separate instantiations keep each variant's register footprint below the 168-register cap
+template <bool kPair, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ GemmKParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -103,26 +111,31 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     const int b_rows = kPair ? (BN >> 1) : BN;                      // B rows staged by THIS CTA
     const uint32_t b_stage_bytes = (uint32_t)b_rows * 128u;
 
+    const int main_kblocks = p.taps * p.kc_per_tap;
     uint8_t* sA = smem;
     uint8_t* sB = smem + (size_t)S * kAStageBytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + (size_t)S * b_stage_bytes);
+    // B ring (one slot per stage) or, b_resident, one slot per k-block of the N tile
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + (size_t)(p.b_resident ? main_kblocks : S) * b_stage_bytes);
     uint64_t* empty_bar = full_bar + S;
     uint64_t* tfull_bar = empty_bar + S;   // [2]
     uint64_t* tempty_bar = tfull_bar + 2;  // [2]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* bfull_bar = tempty_bar + 2;  // resident B loaded
+    uint64_t* bfree_bar = bfull_bar + 1;   // every MMA reading the resident B has retired
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bfree_bar + 1);
     // epilogue staging of the per-column vectors (bias, folded-LayerNorm u): [2 accumulators][bias 256 | u 256] floats
     float* s_epi = reinterpret_cast<float*>(tmem_ptr_smem + 4);
     // output staging for the TMA-store epilogue: one 128-row x 32-column (64 B, 64B-swizzled) box per column group
     uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_epi + 1024) + 1023) & ~uintptr_t(1023));
+    // 64 x 64 identity (K-major, 128B-swizzled like a weight tile): the B operand of the residual k-blocks
+    uint8_t* s_eye = s_stage + 16384;
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&p.tmA);
         tc::tma_prefetch_desc(&p.tmB);
         if (p.res_kblocks) {
             tc::tma_prefetch_desc(&p.tmR);
-            tc::tma_prefetch_desc(&p.tmE);
         }
-        if (p.tma_store) tc::tma_prefetch_desc(&p.tmO);
+        if (p.tma_store) tc::tma_prefetch_desc(p.warp_box ? &p.tmOw : &p.tmO);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < S; ++s) {
@@ -133,6 +146,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             tc::mbar_init(&tfull_bar[a], 1);
             tc::mbar_init(&tempty_bar[a], kPair ? 16 : 8);   // epilogue warps of both CTAs release the leader
         }
+        tc::mbar_init(bfull_bar, 1);
+        tc::mbar_init(bfree_bar, 1);
         tc::fence_mbar_init();
     }
     if (warp == 2) {
@@ -144,6 +159,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             tc::tmem_relinquish();
         }
     }
+    if (p.res_kblocks && warp >= 2) {
+        // this CTA's rows of the identity: a pair splits B by rows (32 each), a single CTA holds all 64
+        const int e = (int)threadIdx.x - 64;                       // 0..255
+        const int rows = kPair ? 32 : 64;
+        for (int i = e; i < rows * 8; i += 256) reinterpret_cast<uint4*>(s_eye)[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (e < rows) {
+            const int k = (kPair ? (int)rank * 32 : 0) + e;        // column holding the 1 of local row e
+            *reinterpret_cast<__half*>(s_eye + e * 128 + (((k >> 3) ^ (e & 7)) << 4) + (k & 7) * 2) = __float2half(1.f);
+        }
+        tc::fence_proxy_async_smem();
+    }
     tc::tc_fence_before();
     if constexpr (kPair) tc::cluster_sync_all(); else __syncthreads();
     tc::tc_fence_after();
@@ -154,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     const int n_units = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int tiles_mu = kPair ? ((p.tiles_m + 1) >> 1) : p.tiles_m;
     const int total_tiles = tiles_mu * p.tiles_nn;
-    const int kblocks = p.taps * p.kc_per_tap + p.res_kblocks;   // consumer view (residual k-blocks included)
+    const int kblocks = main_kblocks + p.res_kblocks;   // consumer view (residual k-blocks included)
     // tile -> (nt, mt) for this CTA; mt >= tiles_m (odd tail of a pair) decodes to out-of-range coordinates:
     // its TMA boxes are zero-filled and its rows are never stored
 #define TC_DECODE_TILE(tile)                                                   \
@@ -172,9 +199,34 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = unit; tile < total_tiles; tile += n_units) {
+            int cur_nt = -1;
+            uint32_t bphase = 0;
+            int ti = 0;
+            for (int tile = unit; tile < total_tiles; tile += n_units, ++ti) {
                 TC_DECODE_TILE(tile)
                 const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+                if (lane == 0) { TC_TRACE(0, ti) }
+                if (p.b_resident && nt != cur_nt) {
+                    // (re)load the weight N-tile: skinny GEMMs (M >> N, short K) otherwise re-fetch it from L2 for every
+                    // M tile, which is more traffic than A itself and runs into the ~6300 B/clk chip-wide L2 cap
+                    tc::mbar_wait(bfree_bar, bphase ^ 1u);
+                    if (tc::elect_one()) {
+                        const uint32_t bytes = (uint32_t)main_kblocks * b_stage_bytes;
+                        if constexpr (kPair) {
+                            if (rank == 0) tc::mbar_arrive_expect_tx(bfull_bar, 2u * bytes);
+                            for (int kb = 0; kb < main_kblocks; ++kb)
+                                tc::tma_load_2d_pair(sB + (size_t)kb * b_stage_bytes, &p.tmB, bfull_bar, kb * kBlockK,
+                                                     nt * BN + (int)rank * b_rows);
+                        } else {
+                            tc::mbar_arrive_expect_tx(bfull_bar, bytes);
+                            for (int kb = 0; kb < main_kblocks; ++kb)
+                                tc::tma_load_2d(sB + (size_t)kb * b_stage_bytes, &p.tmB, bfull_bar, kb * kBlockK, nt * BN);
+                        }
+                    }
+                    __syncwarp();
+                    cur_nt = nt;
+                    bphase ^= 1u;
+                }
                 for (int tap = 0; tap < p.taps; ++tap) {
                     const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap], an = n0 + p.tap_dn[tap];
                     for (int kc = 0; kc < p.kc_per_tap; ++kc) {
@@ -183,15 +235,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                             uint8_t* dA = sA + (size_t)stage * kAStageBytes;
                             uint8_t* dB = sB + (size_t)stage * b_stage_bytes;
                             const int kcol = (tap * p.kc_per_tap + kc) * kBlockK;
+                            const uint32_t bytes = p.a_bytes + (p.b_resident ? 0u : b_stage_bytes);
                             if constexpr (kPair) {
                                 // both CTAs' bytes are credited to the leader's barrier
-                                if (rank == 0) tc::mbar_arrive_expect_tx(&full_bar[stage], 2u * (p.a_bytes + b_stage_bytes));
+                                if (rank == 0) tc::mbar_arrive_expect_tx(&full_bar[stage], 2u * bytes);
                                 tc::tma_load_4d_pair(dA, &p.tmA, &full_bar[stage], kc * kBlockK, ax, ay, an);
-                                tc::tma_load_2d_pair(dB, &p.tmB, &full_bar[stage], kcol, nt * BN + (int)rank * b_rows);
+                                if (!p.b_resident)
+                                    tc::tma_load_2d_pair(dB, &p.tmB, &full_bar[stage], kcol, nt * BN + (int)rank * b_rows);
                             } else {
-                                tc::mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + b_stage_bytes);
+                                tc::mbar_arrive_expect_tx(&full_bar[stage], bytes);
                                 tc::tma_load_4d(dA, &p.tmA, &full_bar[stage], kc * kBlockK, ax, ay, an);
-                                tc::tma_load_2d(dB, &p.tmB, &full_bar[stage], kcol, nt * BN);
+                                if (!p.b_resident) tc::tma_load_2d(dB, &p.tmB, &full_bar[stage], kcol, nt * BN);
                             }
                         }
                         __syncwarp();
@@ -201,21 +255,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                         }
                     }
                 }
-                // residual as extra k-blocks: out += R[tile rows][tile cols] @ I  (TMA-coalesced, fully async; loading it
-                // from registers in the epilogue cost 32 us of a 81 us launch at M=81920, N=K=320: prof_epilogue.py)
+                // residual as extra k-blocks: acc[:, 64r:64r+64] += R[tile rows][64r:64r+64] @ I64  (TMA-coalesced, fully
+                // async; loading it from registers in the epilogue cost 32 us of a 81 us launch at M=81920, N=K=320)
                 for (int r = 0; r < p.res_kblocks; ++r) {
                     tc::mbar_wait(&empty_bar[stage], phase ^ 1u);
                     if (tc::elect_one()) {
-                        uint8_t* dA = sA + (size_t)stage * kAStageBytes;
-                        uint8_t* dB = sB + (size_t)stage * b_stage_bytes;
+                        uint8_t* dA = sA + (size_t)stage * kAStageBytes;   // A slot only: B is the resident identity
                         if constexpr (kPair) {
-                            if (rank == 0) tc::mbar_arrive_expect_tx(&full_bar[stage], 2u * (p.a_bytes + b_stage_bytes));
+                            if (rank == 0) tc::mbar_arrive_expect_tx(&full_bar[stage], 2u * p.a_bytes);
                             tc::tma_load_4d_pair(dA, &p.tmR, &full_bar[stage], nt * BN + r * kBlockK, x0, y0, n0);
-                            tc::tma_load_2d_pair(dB, &p.tmE, &full_bar[stage], r * kBlockK, (int)rank * b_rows);
                         } else {
-                            tc::mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + b_stage_bytes);
+                            tc::mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes);
                             tc::tma_load_4d(dA, &p.tmR, &full_bar[stage], nt * BN + r * kBlockK, x0, y0, n0);
-                            tc::tma_load_2d(dB, &p.tmE, &full_bar[stage], r * kBlockK, 0);
                         }
                     }
                     __syncwarp();
@@ -224,6 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                         phase ^= 1u;
                     }
                 }
+                if (lane == 0) { TC_TRACE(1, ti) }
             }
         }
     } else if (warp == 1) {
@@ -232,29 +284,44 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             const uint32_t idesc = tc::umma_idesc_f16(kPair ? 2 * kBlockM : kBlockM, (uint32_t)BN, 0, 0);
             const uint64_t a_desc0 = tc::umma_desc_sw128(tc::smem_u32(sA));
             const uint64_t b_desc0 = tc::umma_desc_sw128(tc::smem_u32(sB));
+            const uint64_t eye_desc = tc::umma_desc_sw128(tc::smem_u32(s_eye));
+            const uint32_t idesc_eye = tc::umma_idesc_f16(kPair ? 2 * kBlockM : kBlockM, 64u, 0, 0);
             const uint64_t a_step = (uint64_t)(kAStageBytes >> 4), b_step = (uint64_t)(b_stage_bytes >> 4);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = unit; tile < total_tiles; tile += n_units) {
+            int cur_nt = -1;
+            uint32_t bphase = 0;
+            int ti = 0;
+            for (int tile = unit; tile < total_tiles; tile += n_units, ++ti) {
+                if (p.b_resident && tile / tiles_mu != cur_nt) {
+                    tc::mbar_wait(bfull_bar, bphase);
+                    bphase ^= 1u;
+                    cur_nt = tile / tiles_mu;
+                }
                 tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
                 tc::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
+                if (lane == 0) { TC_TRACE(2, ti) }
                 for (int kb = 0; kb < kblocks; ++kb) {
                     tc::mbar_wait(&full_bar[stage], phase);
                     tc::tc_fence_after();
+                    if (kb == 0 && lane == 0) { TC_TRACE(3, ti) }
                     if (tc::elect_one()) {
+                        const int r = kb - main_kblocks;     // >= 0: residual k-block, N = 64 onto columns [64 r, 64 r + 64)
                         const uint64_t a_desc = a_desc0 + a_step * (uint64_t)stage;
-                        const uint64_t b_desc = b_desc0 + b_step * (uint64_t)stage;
+                        const uint64_t b_desc = r >= 0 ? eye_desc : b_desc0 + b_step * (uint64_t)(p.b_resident ? kb : stage);
+                        const uint32_t id = r >= 0 ? idesc_eye : idesc;
+                        const uint32_t dcol = d_tmem + (r >= 0 ? (uint32_t)(r * 64) : 0u);
 #pragma unroll
                         for (int k = 0; k < kBlockK / 16; ++k) {
                             // advance 16 halfs = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
                             if constexpr (kPair)
-                                tc::umma_f16_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                tc::umma_f16_pair(dcol, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), id,
                                                   (kb | k) != 0 ? 1u : 0u);
                             else
-                                tc::umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                tc::umma_f16(dcol, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), id,
                                              (kb | k) != 0 ? 1u : 0u);
                         }
                         if constexpr (kPair) tc::umma_commit_pair(&empty_bar[stage]); else tc::umma_commit(&empty_bar[stage]);
@@ -267,8 +334,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 }
                 if (tc::elect_one()) {
                     if constexpr (kPair) tc::umma_commit_pair(&tfull_bar[acc]); else tc::umma_commit(&tfull_bar[acc]);
+                    // last tile on this weight N-tile: tell the producer(s) when its MMAs have drained
+                    const int next = tile + n_units;
+                    if (p.b_resident && next < total_tiles && next / tiles_mu != cur_nt) {
+                        if constexpr (kPair) tc::umma_commit_pair(bfree_bar); else tc::umma_commit(bfree_bar);
+                    }
                 }
                 __syncwarp();
+                if (lane == 0) { TC_TRACE(4, ti) }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
@@ -285,21 +358,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         const int rx = row % p.TW;
         const int ry = (row / p.TW) % p.TH;
         const int rn = row / (p.TW * p.TH);
-        const bool geglu = (p.flags & TC_EPI_GEGLU) != 0;
+        const bool geglu = kEpi == 1 || (kEpi == 2 && (p.flags & TC_EPI_GEGLU) != 0);
         const int width = geglu ? (BN >> 1) : BN;                   // output columns per tile
         const int split = ((width / 16 + 1) / 2) * 16;              // group 0: [0, split), group 1: [split, width)
         const int c_begin = cg == 0 ? 0 : split;
         const int c_end = cg == 0 ? split : width;
         const bool vec_ok = (p.n_cols % 16) == 0;                   // all chunks complete -> 16-byte paths
         // TMA-store path: 32-column chunks, chunk k belongs to column group k & 1
-        const bool tma_out = p.tma_store != 0;
-        uint8_t* stg = s_stage + cg * 8192;
-        const bool store_leader = (warp == 2 + 4 * cg) && lane == 0;
-        const uint32_t stg_row = tc::smem_u32(stg) + (uint32_t)row * 64u;
+        constexpr bool tma_out = kEpi != 2;
+        // staging: one 128-row box per column group, or (warp_box) one 32-row box per warp
+        const bool warp_box = p.warp_box != 0;
+        uint8_t* stg = warp_box ? s_stage + (warp - 2) * 2048 : s_stage + cg * 8192;
+        const bool store_leader = warp_box ? (lane == 0) : ((warp == 2 + 4 * cg) && lane == 0);
+        const uint32_t stg_row = tc::smem_u32(stg) + (uint32_t)(warp_box ? lane : row) * 64u;
         const uint32_t stg_swz = (uint32_t)((row >> 1) & 3);
+        // first row of this warp inside the tile box (warp_box: the origin of its store box)
+        const int wx = (q * 32) % p.TW, wy = ((q * 32) / p.TW) % p.TH, wn = (q * 32) / (p.TW * p.TH);
+        const bool warp_rows_in_tile = q * 32 < p.TW * p.TH * p.TN;
+        int staged_nt = -1, sb = 1;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = unit; tile < total_tiles; tile += n_units) {
+        int ti = 0;
+        for (int tile = unit; tile < total_tiles; tile += n_units, ++ti) {
             TC_DECODE_TILE(tile)
             const int x = tx * p.TW + rx, y = ty * p.TH + ry, n = tn * p.TN + rn;
             const bool row_ok = (rn < p.TN) && (x < p.oW) && (y < p.oH) && (n < p.oN);
@@ -314,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             }
             // ---- residual prefetch (up to 128 columns = 16 x 16 B per thread)
             uint4 rres[16];
-            if (rrow && vec_ok && !tma_out) {
+            if (kEpi == 2 && rrow && vec_ok) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int c = c_begin + j * 8;
@@ -322,26 +402,34 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 }
             }
 
-            // ---- per-column vectors of this N tile -> smem (global latency hidden behind the tile's mainloop; reading
-            // them with __ldg after the TMEM load put an L2 round trip on every 16-column chunk: profiles/r01_ncu_lin320)
-            float* sbias = s_epi + acc * 512;
-            float* su = sbias + 256;
-            {
+            // ---- per-column vectors of this N tile -> smem, (re)staged only when the N tile changes (global latency
+            // hidden behind the tile's mainloop; reading them with __ldg after the TMEM load put an L2 round trip on
+            // every 16-column chunk: profiles/r01_ncu_lin320).  Two buffers: a warp that runs ahead writes the other one.
+            const bool restage = nt != staged_nt;
+            if (restage) {
+                sb ^= 1;
+                staged_nt = nt;
+                float* wb = s_epi + sb * 512;
                 const int e = (int)threadIdx.x - 64;            // 0..255 over the 8 epilogue warps
                 const int col = nt * BN + e;
                 const bool ok = e < BN && col < p.n_cols;
-                if (p.bias) sbias[e] = ok ? __ldg(p.bias + col) : 0.f;
-                if (p.ln_u) su[e] = ok ? __ldg(p.ln_u + col) : 0.f;
+                if (p.bias) wb[e] = ok ? __ldg(p.bias + col) : 0.f;
+                if (p.ln_u) wb[256 + e] = ok ? __ldg(p.ln_u + col) : 0.f;
             }
+            float* sbias = s_epi + sb * 512;
+            float* su = sbias + 256;
 
+            if (threadIdx.x == 64) { TC_TRACE(5, ti) }
             tc::mbar_wait(&tfull_bar[acc], acc_phase);
             tc::tc_fence_after();
-            asm volatile("bar.sync 1, 256;" ::: "memory");       // staging visible to all epilogue warps
+            if (threadIdx.x == 64) { TC_TRACE(6, ti) }
+            if (restage) asm volatile("bar.sync 1, 256;" ::: "memory");       // staging visible to all epilogue warps
+            if (threadIdx.x == 64) { TC_TRACE(15, ti) }
             const uint32_t taddr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(q * 32) << 16);
 
             if (g_tc_gemm_debug & 2) {
                 // (profiling) accumulator is dropped: measures mainloop + handshake only
-            } else if (tma_out) {
+            } else if constexpr (kEpi != 2) {
                 // ---- TMEM -> registers -> swizzled smem box -> one TMA store per 128 x 32 chunk.  Per-thread 16-byte
                 // global stores touch 32 different lines per instruction (LSU: 16 B/clk instead of 128 B/clk) and cost
                 // 30-35 % of the K = 320 launches (scripts/prof_epilogue.py, mode 0 vs 1).
@@ -349,21 +437,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 const __half* b2row =
                     p.bias2 ? p.bias2 + (row_ok ? (m / p.bias2_rows_per) : 0) * p.bias2_ld + (long long)nt * BN : nullptr;
                 const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+                const int dbg = g_tc_gemm_debug;
+                uint32_t r[32];
+                if (kEpi == 0 && cg * 32 < width) tc::tmem_ld32(taddr + (uint32_t)(cg * 32), r);
 #pragma unroll 1
                 for (int jc = 0; jc < 4; ++jc) {
                     const int c = (cg + 2 * jc) * 32;
                     if (c >= width) break;
-                    float v[32];
-                    if (!geglu) {
-                        // register-path residual (long K loops / scaled accumulators only: the epilogue has slack there)
+                    uint32_t pk[16];                                   // the chunk's 32 outputs of this row, fp16 pairs
+                    if constexpr (kEpi == 0) {
+                        // register-path residual (scaled accumulators only; otherwise it rides the tensor core)
                         uint4 rr[4];
                         if (rrow) {
 #pragma unroll
                             for (int hh = 0; hh < 4; ++hh) rr[hh] = *reinterpret_cast<const uint4*>(rrow + c + hh * 8);
                         }
-                        uint32_t r[32];
-                        tc::tmem_ld32(taddr + (uint32_t)c, r);
                         tc::tmem_ld_wait();
+                        float v[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
                         if (p.ln_u) {
@@ -406,8 +496,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                         if (rrow) {
 #pragma unroll
                             for (int hh = 0; hh < 4; ++hh) {
-                                const uint4 u = rr[hh];
-                                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+                                const __half2* h2 = reinterpret_cast<const __half2*>(&rr[hh]);
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
                                     const float2 f = __half22float2(h2[i]);
@@ -416,6 +505,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                                 }
                             }
                         }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                            pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                        // next chunk's accumulator read flies while this one is staged and stored
+                        if (c + 64 < width) tc::tmem_ld32(taddr + (uint32_t)(c + 64), r);
                     } else {
                         // weight rows of this N tile are [value half (BN/2) | gate half (BN/2)]
 #pragma unroll
@@ -448,32 +544,42 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                                     g2 = ln_rstd * (g2 - ln_mean * ug.z);
                                     g3 = ln_rstd * (g3 - ln_mean * ug.w);
                                 }
-                                v[h16 * 16 + 4 * i] = (a0 + ba.x) * tc::gelu_erf_f(g0 + bg.x);
-                                v[h16 * 16 + 4 * i + 1] = (a1 + ba.y) * tc::gelu_erf_f(g1 + bg.y);
-                                v[h16 * 16 + 4 * i + 2] = (a2 + ba.z) * tc::gelu_erf_f(g2 + bg.z);
-                                v[h16 * 16 + 4 * i + 3] = (a3 + ba.w) * tc::gelu_erf_f(g3 + bg.w);
+                                const __half2 h0 = __floats2half2_rn((a0 + ba.x) * tc::gelu_erf_f(g0 + bg.x),
+                                                                     (a1 + ba.y) * tc::gelu_erf_f(g1 + bg.y));
+                                const __half2 h1 = __floats2half2_rn((a2 + ba.z) * tc::gelu_erf_f(g2 + bg.z),
+                                                                     (a3 + ba.w) * tc::gelu_erf_f(g3 + bg.w));
+                                pk[h16 * 8 + 2 * i] = *reinterpret_cast<const uint32_t*>(&h0);
+                                pk[h16 * 8 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&h1);
                             }
                         }
                     }
-                    // the previous chunk's TMA store must have drained the staging box before it is overwritten
+                    // the previous TMA store must have drained the staging box before it is overwritten
                     if (store_leader) tc::bulk_wait_group_read<0>();
-                    if (cg == 0) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
+                    if (warp_box) __syncwarp();
+                    else if (cg == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+                    else asm volatile("bar.sync 3, 128;" ::: "memory");
+                    if (!(dbg & 16))
 #pragma unroll
                     for (int hh = 0; hh < 4; ++hh) {
-                        __half2 h[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[hh * 8 + 2 * i], v[hh * 8 + 2 * i + 1]);
                         const uint32_t dst = stg_row + ((((uint32_t)hh) ^ stg_swz) << 4);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
-                                     "r"(*reinterpret_cast<uint32_t*>(&h[0])), "r"(*reinterpret_cast<uint32_t*>(&h[1])),
-                                     "r"(*reinterpret_cast<uint32_t*>(&h[2])), "r"(*reinterpret_cast<uint32_t*>(&h[3]))
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * hh]),
+                                     "r"(pk[4 * hh + 1]), "r"(pk[4 * hh + 2]), "r"(pk[4 * hh + 3])
                                      : "memory");
                     }
-                    tc::fence_proxy_async_smem();
-                    if (cg == 0) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
-                    if (store_leader && !(g_tc_gemm_debug & 1)) {
-                        tc::tma_store_4d(stg, &p.tmO, nt * width + c, x0, y0, n0);
-                        tc::bulk_commit_group();
+                    if (!(dbg & 8)) tc::fence_proxy_async_smem();
+                    if (warp_box) __syncwarp();
+                    else if (cg == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+                    else asm volatile("bar.sync 3, 128;" ::: "memory");
+                    if (store_leader && !(dbg & 1)) {
+                        if (warp_box) {
+                            if (warp_rows_in_tile) {
+                                tc::tma_store_4d(stg, &p.tmOw, nt * width + c, x0 + wx, y0 + wy, n0 + wn);
+                                tc::bulk_commit_group();
+                            }
+                        } else {
+                            tc::tma_store_4d(stg, &p.tmO, nt * width + c, x0, y0, n0);
+                            tc::bulk_commit_group();
+                        }
                     }
                 }
             } else if (!geglu) {
@@ -610,32 +716,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             if (lane == 0) {
                 if constexpr (kPair) tc::mbar_arrive_cluster(&tempty_bar[acc], 0); else tc::mbar_arrive(&tempty_bar[acc]);
             }
+            if (threadIdx.x == 64) { TC_TRACE(7, ti) }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
     }
 #undef TC_DECODE_TILE
 
-    if (p.tma_store && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) tc::bulk_wait_group<0>();
+    if (p.tma_store && warp >= 2 && lane == 0) tc::bulk_wait_group<0>();
     tc::tc_fence_before();
     if constexpr (kPair) tc::cluster_sync_all(); else __syncthreads();   // the peer may still read our smem / barriers
     if (warp == 2) {
         tc::tc_fence_after();
         if constexpr (kPair) tc::tmem_dealloc_pair(tmem_base, kTmemCols); else tc::tmem_dealloc(tmem_base, kTmemCols);
     }
-}
-
-// 256 x 256 fp16 identity used as the B operand of the residual k-blocks (lazily created once per process; the only
-// device allocation this library ever makes)
-const __half* identity_table() {
-    static __half* dev = nullptr;
-    if (!dev) {
-        std::vector<__half> h(256 * 256, __float2half(0.f));
-        for (int i = 0; i < 256; ++i) h[i * 256 + i] = __float2half(1.f);
-        if (cudaMalloc(&dev, h.size() * sizeof(__half)) != cudaSuccess) return nullptr;
-        if (cudaMemcpy(dev, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
-    }
-    return dev;
 }
 
 // Tile-shape heuristic: pick (block_n, single / CTA-pair) minimising   waves x per-tile cycles   with a small model
@@ -677,6 +771,13 @@ TileChoice choose_tiles(int tiles_m, int n_cols, int kblocks, int forced_bn, int
 }
 
 }  // namespace
+
+extern "C" int tc_debug_read_gemm_trace(unsigned long long* host_dst, int count) {
+    if (!host_dst || count <= 0 || count > kTraceCtas * kTraceTiles * kTraceSlots)
+        return tc_host::fail(TC_ERR_INVALID, "tc_debug_read_gemm_trace: bad count");
+    return tc_host::check_cuda(cudaMemcpyFromSymbol(host_dst, g_tc_gemm_trace, (size_t)count * sizeof(unsigned long long)),
+                               "tc_debug_read_gemm_trace");
+}
 
 extern "C" int tc_debug_set_gemm_mode(int mode) {
     return tc_host::check_cuda(cudaMemcpyToSymbol(g_tc_gemm_debug, &mode, sizeof(int)), "tc_debug_set_gemm_mode");
@@ -790,26 +891,19 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
         p.tmB = *m;
     }
 
-    // residual through the tensor core when the K loop is short (epilogue-bound regime) and no scaling is involved
     const int main_kblocks = d->taps * (d->a_C / kBlockK);
+    // residual through the tensor core (extra A-only k-blocks against a shared-memory identity) unless it must stay
+    // outside the accumulator scaling
     static const char* resmma_env = getenv("TC_GEMM_RES_MMA");   // "0" disables (A/B testing)
-    if (d->res && !geglu && d->acc_scale == 1.0f && main_kblocks <= 24 && d->n_cols % 8 == 0 &&
-        !(resmma_env && resmma_env[0] == '0')) {
-        const __half* eye = identity_table();
-        if (!eye) return fail(TC_ERR_CUDA, "tc_conv_gemm: identity table allocation failed");
+    if (d->res && !geglu && d->acc_scale == 1.0f && d->n_cols % 8 == 0 && !(resmma_env && resmma_env[0] == '0')) {
         p.res_kblocks = (BN + kBlockK - 1) / kBlockK;
         uint64_t rdims[4] = {(uint64_t)d->n_cols, (uint64_t)d->oW, (uint64_t)d->oH, (uint64_t)d->oN};
         uint64_t rstr[3] = {(uint64_t)d->ldr * 2, (uint64_t)d->oW * (uint64_t)d->ldr * 2,
                             (uint64_t)d->oH * (uint64_t)d->oW * (uint64_t)d->ldr * 2};
         uint32_t rbox[4] = {(uint32_t)kBlockK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
         const CUtensorMap* mr = get_tensor_map(d->res, 4, rdims, rstr, rbox);
-        uint64_t edims[2] = {256, 256};
-        uint64_t estr[1] = {256 * 2};
-        uint32_t ebox[2] = {(uint32_t)kBlockK, (uint32_t)(pair ? BN / 2 : BN)};
-        const CUtensorMap* me = get_tensor_map(eye, 2, edims, estr, ebox);
-        if (!mr || !me) return TC_ERR_CUDA;
+        if (!mr) return TC_ERR_CUDA;
         p.tmR = *mr;
-        p.tmE = *me;
     }
     // TMA-store epilogue: whole 32-column chunks of 16-byte-aligned rows
     {
@@ -825,54 +919,88 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
             if (!mo) return TC_ERR_CUDA;
             p.tmO = *mo;
             p.tma_store = 1;
+            // do the 32 rows of an epilogue warp form a box of the output tensor?
+            int wbW = 0, wbH = 0, wbN = 0;
+            if (p.TW % 32 == 0) {
+                wbW = 32, wbH = 1, wbN = 1;
+            } else if (32 % p.TW == 0) {
+                const int rows = 32 / p.TW;
+                if (p.TH % rows == 0) wbW = p.TW, wbH = rows, wbN = 1;
+                else if (rows % p.TH == 0 && p.TN % (rows / p.TH) == 0) wbW = p.TW, wbH = p.TH, wbN = rows / p.TH;
+            }
+            static const char* wbox_env = getenv("TC_GEMM_WARP_BOX");   // "0" disables (A/B testing)
+            if (wbW && (p.TW * p.TH * p.TN) % 32 == 0 && !(wbox_env && wbox_env[0] == '0')) {
+                uint32_t wbox[4] = {32u, (uint32_t)wbW, (uint32_t)wbH, (uint32_t)wbN};
+                const CUtensorMap* mw = get_tensor_map(d->out, 4, odims, ostr, wbox, 64);
+                if (!mw) return TC_ERR_CUDA;
+                p.tmOw = *mw;
+                p.warp_box = 1;
+            }
         }
     }
     const int stage_bytes = kAStageBytes + (pair ? BN / 2 : BN) * 128;
-    const int kFixedSmem = 1024 + 512 + 4096 + 1024 + 16384;   // alignment slack, barriers, epilogue vectors, store staging
+    // alignment slack, barriers, epilogue vectors, store staging, identity tile
+    const int kFixedSmem = 1024 + 512 + 4096 + 1024 + 16384 + 8192;
     const int smem_budget = 227 * 1024 - kFixedSmem;
     int stages = smem_budget / stage_bytes;
     if (stages > 8) stages = 8;
+    // weight-resident mode: short K loops whose N tile fits beside >= 5 A stages, when a CTA sees several M tiles
+    static const char* bres_env = getenv("TC_GEMM_BRES");   // "0" disables (A/B testing)
+    {
+        const long long units = pair ? pair_tiles : (long long)p.tiles_m * p.tiles_nn;
+        const int slots = pair ? sm_count() / 2 : sm_count();
+        const int bres_bytes = main_kblocks * (pair ? BN / 2 : BN) * 128;
+        const int a_stages = (smem_budget - bres_bytes) / kAStageBytes;
+        if (bres_bytes < smem_budget && a_stages >= 5 && units >= 3LL * slots && !(bres_env && bres_env[0] == '0')) {
+            p.b_resident = 1;
+            stages = a_stages > 12 ? 12 : a_stages;
+        }
+    }
     if (stages < 2) return fail(TC_ERR_INVALID, "tc_conv_gemm: not enough shared memory for 2 stages");
     p.stages = stages;
-    const size_t smem_bytes = (size_t)stages * stage_bytes + kFixedSmem;
+    const size_t smem_bytes = (p.b_resident ? (size_t)stages * kAStageBytes + (size_t)main_kblocks * (pair ? BN / 2 : BN) * 128
+                                            : (size_t)stages * stage_bytes) + kFixedSmem;
 
+    const int epi = !p.tma_store ? 2 : (geglu ? 1 : 0);
+    using KernelFn = void (*)(GemmKParams);
+    static const KernelFn kernels[2][3] = {
+        {tc_gemm_kernel<false, 0>, tc_gemm_kernel<false, 1>, tc_gemm_kernel<false, 2>},
+        {tc_gemm_kernel<true, 0>, tc_gemm_kernel<true, 1>, tc_gemm_kernel<true, 2>}};
     static bool attr_set = false;
     if (!attr_set) {
-        int rc = check_cuda(
-            cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-            "cudaFuncSetAttribute(tc_gemm_kernel<false>)");
-        if (rc) return rc;
-        rc = check_cuda(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-                        "cudaFuncSetAttribute(tc_gemm_kernel<true>)");
-        if (rc) return rc;
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 3; ++b) {
+                int rc = check_cuda(cudaFuncSetAttribute(reinterpret_cast<const void*>(kernels[a][b]),
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                                    "cudaFuncSetAttribute(tc_gemm_kernel)");
+                if (rc) return rc;
+            }
         attr_set = true;
     }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
     if (pair) {
         int units = sm_count() / 2;
         if (pair_tiles < units) units = (int)pair_tiles;
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(2 * units);
-        cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = smem_bytes;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        int rc = check_cuda(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<true>, p), "tc_gemm_kernel<pair> launch");
-        count_launch();
-        if (rc) return rc;
     } else {
         const long long total_tiles = (long long)p.tiles_m * p.tiles_nn;
         int grid = sm_count();
         if (total_tiles < grid) grid = (int)total_tiles;
-        tc_gemm_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(p);
-        count_launch();
-        TC_CHECK_LAUNCH("tc_gemm_kernel launch");
+        cfg.gridDim = dim3(grid);
     }
+    int rc = check_cuda(cudaLaunchKernelEx(&cfg, kernels[pair ? 1 : 0][epi], p), "tc_gemm_kernel launch");
+    count_launch();
+    if (rc) return rc;
     return TC_OK;
 }
