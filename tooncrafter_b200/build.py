@@ -23,6 +23,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
 ]
+if os.environ.get("TC_BUILD_TRACE") == "1":      # in-kernel role timeline for scripts/trace_gemm.py (slows the kernels)
+    NVCC_FLAGS.append("-DTC_GEMM_TRACE=1")
 
 
 def _nvcc() -> str:

@@ -49,6 +49,7 @@ constexpr int kAttnTmemCols = 512;  // S0 [0,128) S1 [128,256) O0 [256,320) O1 [
 
 template <bool kTwoSeg>
 __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_constant__ AttnKParams p) {
+    tc::pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                     // 2 tiles
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    tc::pdl_wait();   // prologue (barriers, TMEM) overlapped the predecessor; Q/K/V are its results
 
     if (warp == 9) {
         // ------------------------------------------------------------------------------ TMA producer
@@ -368,6 +370,8 @@ template <int kGroup>
 __global__ void temporal_attn_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
                                      const __half* __restrict__ v, long long ld, __half* __restrict__ out,
                                      long long ldo, int B, int T, int P, int heads, float scale_log2) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     constexpr int kItemsPerWarp = 32 / kGroup;
     constexpr int kWarps = 4;
     __shared__ __align__(16) __half sK[kWarps * kItemsPerWarp][kGroup][64];
@@ -482,6 +486,8 @@ __global__ void __launch_bounds__(128) temporal_attn_mma_kernel(const __half* __
                                                                 const __half* __restrict__ v, long long ld,
                                                                 __half* __restrict__ out, long long ldo, int B, int T,
                                                                 int P, int heads, float scale_log2) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     __shared__ __align__(128) uint8_t sV[4][16 * 128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t4 = lane & 3;
@@ -599,6 +605,8 @@ __global__ void __launch_bounds__(128) temporal_attn_mma_kernel(const __half* __
 
 // ===================================================================================== row softmax (in place)
 __global__ void softmax_rows_kernel(__half* __restrict__ s, long long lds, int rows, int cols, float scale_log2) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     const int row = blockIdx.x;
     if (row >= rows) return;
     __half* r = s + (long long)row * lds;
@@ -682,9 +690,9 @@ extern "C" int tc_attention(const TcAttention* d, void* stream_v) {
     }
     dim3 grid((d->Lq + 2 * kQTile - 1) / (2 * kQTile), d->heads, d->q_batches);
     if (d->n_seg == 2)
-        tc_attn_kernel<true><<<grid, kAttnThreads, smem_bytes, stream>>>(p);
+        tc_host::launch(tc_attn_kernel<true>, dim3(grid), dim3(kAttnThreads), smem_bytes, stream, 1, p);
     else
-        tc_attn_kernel<false><<<grid, kAttnThreads, smem_bytes, stream>>>(p);
+        tc_host::launch(tc_attn_kernel<false>, dim3(grid), dim3(kAttnThreads), smem_bytes, stream, 1, p);
     count_launch();
     TC_CHECK_LAUNCH("tc_attn_kernel");
     return TC_OK;
@@ -706,10 +714,10 @@ extern "C" int tc_temporal_attention(const void* q, const void* k, const void* v
         long long blocks = (items + 3) / 4;
         const long long cap = 16LL * sm_count();
         if (blocks > cap) blocks = cap;
-        temporal_attn_mma_kernel<<<(unsigned)blocks, 128, 0, stream>>>(qp, kp, vp, ld, op, ldo, B, T, P, heads, sl2);
+        tc_host::launch(temporal_attn_mma_kernel, dim3((unsigned)blocks), dim3(128), 0, stream, 1, qp, kp, vp, ld, op, ldo, B, T, P, heads, sl2);
     } else {
         const long long blocks = (items + 3) / 4;
-        temporal_attn_kernel<32><<<(unsigned)blocks, 128, 0, stream>>>(qp, kp, vp, ld, op, ldo, B, T, P, heads, sl2);
+        tc_host::launch(temporal_attn_kernel<32>, dim3((unsigned)blocks), dim3(128), 0, stream, 1, qp, kp, vp, ld, op, ldo, B, T, P, heads, sl2);
     }
     count_launch();
     TC_CHECK_LAUNCH("temporal_attn_kernel");
@@ -719,7 +727,7 @@ extern "C" int tc_temporal_attention(const void* q, const void* k, const void* v
 extern "C" int tc_softmax_rows(void* s, long long lds, int rows, int cols, float scale, void* stream_v) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     TC_CHECK_ARG(s && rows > 0 && cols > 0, "tc_softmax_rows: bad arguments");
-    softmax_rows_kernel<<<rows, 256, 0, stream>>>(reinterpret_cast<__half*>(s), lds, rows, cols,
+    tc_host::launch(softmax_rows_kernel, dim3(rows), dim3(256), 0, stream, 1, reinterpret_cast<__half*>(s), lds, rows, cols,
                                                   scale * 1.4426950408889634f);
     count_launch();
     TC_CHECK_LAUNCH("softmax_rows_kernel");

@@ -159,6 +159,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// ---- programmatic dependent launch: every kernel of this library is launched with the programmatic-stream-serialization
+// attribute (tc_host::launch), lets its successor's CTAs start early (launch_dependents) and must execute pdl_wait()
+// before its first access to global memory a predecessor may have written — and EVERY kernel must execute it, otherwise
+// completion of kernel N would no longer imply completion of kernel N-1 for kernel N+1.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- TMA stores (shared -> global, bulk async group completion) ---------------------------------------
 __device__ __forceinline__ void tma_store_4d(const void* smem_src, const void* tmap, int c0, int c1, int c2, int c3) {
     asm volatile(

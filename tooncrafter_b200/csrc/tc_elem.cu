@@ -11,6 +11,8 @@ __device__ __forceinline__ void st16(void* p, const uint4& v) { *reinterpret_cas
 // ------------------------------------------------------------------------------------------------ layout
 __global__ void ncthw_to_cl_kernel(const float* __restrict__ x, __half* __restrict__ y, int B, int C, int T, int H,
                                    int W, int Cpad, int coff, float scale) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     const long long npix = (long long)B * T * H * W;
     const long long thw = (long long)T * H * W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
@@ -25,6 +27,8 @@ __global__ void ncthw_to_cl_kernel(const float* __restrict__ x, __half* __restri
 template <typename OutT>
 __global__ void cl_to_ncthw_kernel(const __half* __restrict__ x, long long ldx, OutT* __restrict__ y, int B, int C,
                                    int T, int H, int W) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     const long long npix = (long long)B * T * H * W;
     const long long thw = (long long)T * H * W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
@@ -42,6 +46,8 @@ __global__ void cl_to_ncthw_kernel(const __half* __restrict__ x, long long ldx, 
 }
 
 __global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restrict__ y, int N, int H, int W, int C) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     const int V = C >> 3;
     const long long total = (long long)N * (2 * H) * (2 * W) * V;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -60,6 +66,8 @@ __global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restri
 // y[ph][n][h2][w2][c] = x[n][2*h2 + (ph>>1)][2*w2 + (ph&1)][c]
 __global__ void phase_split2_kernel(const __half* __restrict__ x, __half* __restrict__ y, int N, int H, int W,
                                     int C) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     const int V = C >> 3;
     const int H2 = H >> 1, W2 = W >> 1;
     const long long total = (long long)4 * N * H2 * W2 * V;
@@ -80,6 +88,8 @@ __global__ void phase_split2_kernel(const __half* __restrict__ x, __half* __rest
 
 __global__ void copy2d_kernel(const __half* __restrict__ src, long long lds, __half* __restrict__ dst, long long ldd,
                               long long rows, int cols) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     const int V = cols >> 3;
     const long long total = rows * V;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -92,6 +102,8 @@ __global__ void copy2d_kernel(const __half* __restrict__ src, long long lds, __h
 
 __global__ void add2d_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
                              long long rows, int cols) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     const int V = cols >> 3;
     const long long total = rows * V;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -111,6 +123,8 @@ __global__ void add2d_kernel(const __half* __restrict__ x, long long ldx, __half
 // ------------------------------------------------------------------------------------------------ tiny linears
 // sinusoidal embedding: out[b][0:half] = cos(t*f_i), out[b][half:2*half] = sin(t*f_i), f_i = exp(-ln(1e4)*i/half)
 __global__ void sincos_kernel(const float* __restrict__ t, int B, int dim, float* __restrict__ out) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     const int half = dim / 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
@@ -127,6 +141,8 @@ template <typename OutT>
 __global__ void small_linear_kernel(const float* __restrict__ x, int B, int K, const __half* __restrict__ w,
                                     const float* __restrict__ bias, int J, OutT* __restrict__ y, long long ldy,
                                     int silu_in, int accumulate) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (j >= J) return;
@@ -189,6 +205,8 @@ __device__ __forceinline__ __half cfg_combine(__half ec, __half euc, float s) {
 // partial sums for std(e_c) and std(v): ws[b][blk][4] = {sum_ec, sumsq_ec, sum_v, sumsq_v} (double)
 __global__ void ddim_reduce_kernel(const __half* __restrict__ e_c, const __half* __restrict__ e_uc,
                                    const float* __restrict__ coef, long long n, double* __restrict__ ws) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     const int b = blockIdx.y;
     const float s = coef[0];
     const __half* ec = e_c + (long long)b * n;
@@ -231,6 +249,8 @@ __global__ void ddim_update_kernel(const __half* __restrict__ e_c, const __half*
                                    float* __restrict__ x_prev, float* __restrict__ pred_x0,
                                    const float* __restrict__ coef, long long n, const double* __restrict__ ws,
                                    int nblk) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     const int b = blockIdx.y;
     const float s = coef[0], phi = coef[1], sqrt_ac = coef[2], sqrt_1mac = coef[3], rescale = coef[4],
                 sqrt_aprev = coef[5], dir_coef = coef[6], sigma = coef[7];
@@ -290,7 +310,7 @@ extern "C" int tc_ncthw_to_cl(const float* x, void* y, int B, int C, int T, int 
     TC_CHECK_ARG(x && y && B > 0 && C > 0 && T > 0 && H > 0 && W > 0, "tc_ncthw_to_cl: bad arguments");
     TC_CHECK_ARG(coff >= 0 && coff + C <= Cpad, "tc_ncthw_to_cl: channel slice out of range");
     const long long npix = (long long)B * T * H * W;
-    ncthw_to_cl_kernel<<<grid_for(npix, 256, 8 * sm_count()), 256, 0, stream>>>(x, reinterpret_cast<__half*>(y), B,
+    tc_host::launch(ncthw_to_cl_kernel, dim3(grid_for(npix, 256, 8 * sm_count())), dim3(256), 0, stream, 1, x, reinterpret_cast<__half*>(y), B,
                                                                                 C, T, H, W, Cpad, coff, scale);
     count_launch();
     TC_CHECK_LAUNCH("ncthw_to_cl_kernel");
@@ -304,10 +324,10 @@ extern "C" int tc_cl_to_ncthw(const void* x, long long ldx, void* y, int out_fp3
     const long long npix = (long long)B * T * H * W;
     const int g = grid_for(npix, 256, 8 * sm_count());
     if (out_fp32)
-        cl_to_ncthw_kernel<float><<<g, 256, 0, stream>>>(reinterpret_cast<const __half*>(x), ldx,
+        tc_host::launch(cl_to_ncthw_kernel<float>, dim3(g), dim3(256), 0, stream, 1, reinterpret_cast<const __half*>(x), ldx,
                                                          reinterpret_cast<float*>(y), B, C, T, H, W);
     else
-        cl_to_ncthw_kernel<__half><<<g, 256, 0, stream>>>(reinterpret_cast<const __half*>(x), ldx,
+        tc_host::launch(cl_to_ncthw_kernel<__half>, dim3(g), dim3(256), 0, stream, 1, reinterpret_cast<const __half*>(x), ldx,
                                                           reinterpret_cast<__half*>(y), B, C, T, H, W);
     count_launch();
     TC_CHECK_LAUNCH("cl_to_ncthw_kernel");
@@ -318,7 +338,7 @@ extern "C" int tc_upsample2x(const void* x, void* y, int N, int H, int W, int C,
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     TC_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "tc_upsample2x: bad arguments");
     const long long total = (long long)N * 4 * H * W * (C / 8);
-    upsample2x_kernel<<<grid_for(total, 256, 16 * sm_count()), 256, 0, stream>>>(
+    tc_host::launch(upsample2x_kernel, dim3(grid_for(total, 256, 16 * sm_count())), dim3(256), 0, stream, 1, 
         reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), N, H, W, C);
     count_launch();
     TC_CHECK_LAUNCH("upsample2x_kernel");
@@ -330,7 +350,7 @@ extern "C" int tc_phase_split2(const void* x, void* y, int N, int H, int W, int 
     TC_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && H % 2 == 0 && W % 2 == 0,
                  "tc_phase_split2: bad arguments (H, W must be even, C % 8 == 0)");
     const long long total = (long long)N * H * W * (C / 8);
-    phase_split2_kernel<<<grid_for(total, 256, 16 * sm_count()), 256, 0, stream>>>(
+    tc_host::launch(phase_split2_kernel, dim3(grid_for(total, 256, 16 * sm_count())), dim3(256), 0, stream, 1, 
         reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), N, H, W, C);
     count_launch();
     TC_CHECK_LAUNCH("phase_split2_kernel");
@@ -342,7 +362,7 @@ extern "C" int tc_copy2d(const void* src, long long lds, void* dst, long long ld
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     TC_CHECK_ARG(src && dst && rows > 0 && cols > 0 && cols % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0,
                  "tc_copy2d: bad arguments");
-    copy2d_kernel<<<grid_for(rows * (cols / 8), 256, 16 * sm_count()), 256, 0, stream>>>(
+    tc_host::launch(copy2d_kernel, dim3(grid_for(rows * (cols / 8), 256, 16 * sm_count())), dim3(256), 0, stream, 1, 
         reinterpret_cast<const __half*>(src), lds, reinterpret_cast<__half*>(dst), ldd, rows, cols);
     count_launch();
     TC_CHECK_LAUNCH("copy2d_kernel");
@@ -354,7 +374,7 @@ extern "C" int tc_add2d(const void* x, long long ldx, void* y, long long ldy, lo
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     TC_CHECK_ARG(x && y && rows > 0 && cols > 0 && cols % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0,
                  "tc_add2d: bad arguments");
-    add2d_kernel<<<grid_for(rows * (cols / 8), 256, 16 * sm_count()), 256, 0, stream>>>(
+    tc_host::launch(add2d_kernel, dim3(grid_for(rows * (cols / 8), 256, 16 * sm_count())), dim3(256), 0, stream, 1, 
         reinterpret_cast<const __half*>(x), ldx, reinterpret_cast<__half*>(y), ldy, rows, cols);
     count_launch();
     TC_CHECK_LAUNCH("add2d_kernel");
@@ -368,15 +388,15 @@ extern "C" int tc_time_embed(const float* t, int B, int dim, const void* w1, con
     TC_CHECK_ARG(dim % 8 == 0 && hidden % 8 == 0, "tc_time_embed: dim and hidden must be multiples of 8");
     float* emb = ws;                        // [B][dim]
     float* h1 = ws + (long long)B * dim;    // [B][hidden]
-    sincos_kernel<<<(B * (dim / 2) + 127) / 128, 128, 0, stream>>>(t, B, dim, emb);
+    tc_host::launch(sincos_kernel, dim3((B * (dim / 2) + 127) / 128), dim3(128), 0, stream, 1, t, B, dim, emb);
     count_launch();
     TC_CHECK_LAUNCH("sincos_kernel");
     const int blocks = (hidden * 32 + 255) / 256;
-    small_linear_kernel<float><<<blocks, 256, 0, stream>>>(emb, B, dim, reinterpret_cast<const __half*>(w1), b1,
+    tc_host::launch(small_linear_kernel<float>, dim3(blocks), dim3(256), 0, stream, 1, emb, B, dim, reinterpret_cast<const __half*>(w1), b1,
                                                            hidden, h1, hidden, 0, 0);
     count_launch();
     TC_CHECK_LAUNCH("small_linear_kernel(1)");
-    small_linear_kernel<float><<<blocks, 256, 0, stream>>>(h1, B, hidden, reinterpret_cast<const __half*>(w2), b2,
+    tc_host::launch(small_linear_kernel<float>, dim3(blocks), dim3(256), 0, stream, 1, h1, B, hidden, reinterpret_cast<const __half*>(w2), b2,
                                                            hidden, out, hidden, 1, accumulate);
     count_launch();
     TC_CHECK_LAUNCH("small_linear_kernel(2)");
@@ -388,7 +408,7 @@ extern "C" int tc_small_linear(const float* x, int B, int K, const void* w, cons
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     TC_CHECK_ARG(x && w && y && B > 0 && K > 0 && K % 8 == 0 && J > 0, "tc_small_linear: bad arguments");
     const int blocks = (int)(((long long)J * 32 + 255) / 256);
-    small_linear_kernel<__half><<<blocks, 256, 0, stream>>>(x, B, K, reinterpret_cast<const __half*>(w), bias, J,
+    tc_host::launch(small_linear_kernel<__half>, dim3(blocks), dim3(256), 0, stream, 1, x, B, K, reinterpret_cast<const __half*>(w), bias, J,
                                                             reinterpret_cast<__half*>(y), ldy, silu_in, 0);
     count_launch();
     TC_CHECK_LAUNCH("small_linear_kernel");
@@ -400,12 +420,12 @@ extern "C" int tc_ddim_step(const void* e_c, const void* e_uc, const float* x, c
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     TC_CHECK_ARG(e_c && e_uc && x && noise && x_prev && pred_x0 && coef && ws && B > 0 && n > 1,
                  "tc_ddim_step: bad arguments");
-    ddim_reduce_kernel<<<dim3(TC_DDIM_PARTIALS, B), 256, 0, stream>>>(
+    tc_host::launch(ddim_reduce_kernel, dim3(dim3(TC_DDIM_PARTIALS, B)), dim3(256), 0, stream, 1, 
         reinterpret_cast<const __half*>(e_c), reinterpret_cast<const __half*>(e_uc), coef, n, ws);
     count_launch();
     TC_CHECK_LAUNCH("ddim_reduce_kernel");
     int g = grid_for(n, 256, 4 * sm_count());
-    ddim_update_kernel<<<dim3(g, B), 256, 0, stream>>>(reinterpret_cast<const __half*>(e_c),
+    tc_host::launch(ddim_update_kernel, dim3(dim3(g, B)), dim3(256), 0, stream, 1, reinterpret_cast<const __half*>(e_c),
                                                        reinterpret_cast<const __half*>(e_uc), x, noise, x_prev,
                                                        pred_x0, coef, n, ws, TC_DDIM_PARTIALS);
     count_launch();

@@ -65,9 +65,15 @@ __device__ int g_tc_gemm_debug = 0;   // profiling aid (scripts/prof_epilogue.py
                                       // 4 = record per-tile clock64() stamps of each warp role (scripts/trace_gemm.py)
 constexpr int kTraceTiles = 32, kTraceSlots = 16, kTraceCtas = 160;
 __device__ unsigned long long g_tc_gemm_trace[kTraceCtas * kTraceTiles * kTraceSlots];
+// compiled in only with -DTC_GEMM_TRACE=1 (python tooncrafter_b200/build.py --trace): even the disabled checks cost the
+// long-K convolutions 10-25 % (measured, scripts/ab_conv.py)
+#if defined(TC_GEMM_TRACE) && TC_GEMM_TRACE
 #define TC_TRACE(slot, ti)                                                                                   \
     if ((g_tc_gemm_debug & 4) && (ti) < kTraceTiles && blockIdx.x < kTraceCtas)                                \
         g_tc_gemm_trace[((int)blockIdx.x * kTraceTiles + (ti)) * kTraceSlots + (slot)] = (unsigned long long)clock64();
+#else
+#define TC_TRACE(slot, ti)
+#endif
 
 __device__ __forceinline__ void store_row16(__half* dst, const float (&v)[16], int ncols_valid) {
     if (g_tc_gemm_debug & 1) return;
@@ -100,6 +106,7 @@ __device__ __forceinline__ void store_row16(__half* dst, const float (&v)[16], i
 // odd widths); separate instantiations keep each variant's register footprint below the 168-register cap
 template <bool kPair, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ GemmKParams p) {
+    tc::pdl_launch_dependents();   // the successor's prologue may overlap this kernel; it blocks in its own pdl_wait
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -175,6 +182,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     if constexpr (kPair) tc::cluster_sync_all(); else __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // barriers, TMEM and the identity tile are set up: from here on the kernel touches its predecessors' results
+    tc::pdl_wait();
 
     // work units: a single CTA takes one M tile, a CTA pair takes two consecutive M tiles (rank selects which)
     const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -733,8 +742,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 }
 
 // Tile-shape heuristic: pick (block_n, single / CTA-pair) minimising   waves x per-tile cycles   with a small model
-// measured on B200: an M128 x N x K64 k-block costs max(2 N tensor cycles, ~200 issue cycles), plus ~1500 cycles of
-// per-tile pipeline fill / epilogue tail.  Matters for the 10x16 and 5x8 UNet levels (M = 5120 / 1280 rows), where
+// measured on B200 (tensor rate vs. TMA ingest per k-block, see below), plus ~1500 cycles of per-tile pipeline fill /
+// epilogue tail.  Matters for the 10x16 and 5x8 UNet levels (M = 5120 / 1280 rows), where
 // one wave of 256-wide tiles leaves most SMs idle.
 struct TileChoice {
     int bn;
@@ -753,14 +762,20 @@ TileChoice choose_tiles(int tiles_m, int n_cols, int kblocks, int forced_bn, int
             if (n16 > 256 ? (n16 % bn != 0 || bn < 64 || bn % 32 != 0) : (bn != n16)) continue;
         }
         const int tiles_n = (n_cols + bn - 1) / bn;
-        const double kb_cost = (double)kblocks * (2.0 * bn > 200.0 ? 2.0 * bn : 200.0) + 1500.0 + 4.0 * bn;
         for (int pair = 0; pair < 2; ++pair) {
             if (pair && tiles_m < 2) continue;
+            // one k-block (M128 x bn x K64 per CTA): tensor time ~2.5 bn cycles at the sustained rate, or the TMA ingest
+            // of its operands at the ~52 B/clk/SM the L2 delivers (A 16 KB + B bn x 128 B, halved by a pair) — measured
+            // with scripts/sweep_tiles.py: e.g. conv 640->640 @20x32 runs 148 us with bn 128 and 126 us with bn 160
+            const double tensor = 2.5 * bn;
+            const double ingest = (16384.0 + (double)bn * (pair ? 64.0 : 128.0)) / 52.0;
+            double kb_cycles = tensor > ingest ? tensor : ingest;
+            if (kb_cycles < 200.0) kb_cycles = 200.0;
+            const double tile_cost = (double)kblocks * kb_cycles + 1500.0 + 4.0 * bn;
             const long long units = pair ? (long long)((tiles_m + 1) / 2) * tiles_n : (long long)tiles_m * tiles_n;
             const int slots = pair ? sms / 2 : sms;
             const long long waves = (units + slots - 1) / slots;
-            // the pair shares B between two SMs: ~10 % faster per tile when tensor-bound (measured), never slower
-            const double cost = (double)waves * kb_cost * (pair && 2.0 * bn > 200.0 ? 0.9 : 1.0);
+            const double cost = (double)waves * tile_cost;
             if (cost < best_cost) {
                 best_cost = cost;
                 best = TileChoice{bn, pair != 0};
@@ -977,30 +992,18 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
             }
         attr_set = true;
     }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    int grid;
     if (pair) {
         int units = sm_count() / 2;
         if (pair_tiles < units) units = (int)pair_tiles;
-        cfg.gridDim = dim3(2 * units);
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        grid = 2 * units;
     } else {
         const long long total_tiles = (long long)p.tiles_m * p.tiles_nn;
-        int grid = sm_count();
+        grid = sm_count();
         if (total_tiles < grid) grid = (int)total_tiles;
-        cfg.gridDim = dim3(grid);
     }
-    int rc = check_cuda(cudaLaunchKernelEx(&cfg, kernels[pair ? 1 : 0][epi], p), "tc_gemm_kernel launch");
+    launch(kernels[pair ? 1 : 0][epi], dim3(grid), dim3(kThreads), smem_bytes, stream, pair ? 2 : 1, p);
     count_launch();
-    if (rc) return rc;
+    TC_CHECK_LAUNCH("tc_gemm_kernel launch");
     return TC_OK;
 }

@@ -1,4 +1,5 @@
 // tooncrafter_b200 — error state, launch counter, TMA descriptor cache.
+#include <stdlib.h>
 #include "tc_host.h"
 
 #include <atomic>
@@ -131,6 +132,14 @@ const CUtensorMap* get_tensor_map(const void* base, int rank, const uint64_t* di
     }
     g_maps.emplace(key, m);
     return m;
+}
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("TC_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 
 }  // namespace tc_host

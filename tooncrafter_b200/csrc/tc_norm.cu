@@ -38,6 +38,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // grid = (nblk, n_stat); block = V * k threads (V = C/8), thread t owns channel vector t % V.
 __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ldx, long long pixels_per_stat, int C, int G,
                                 float* __restrict__ partials) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     extern __shared__ float sm[];  // [rows_per_iter][2*C]: per-thread partials, reduced in a fixed order (deterministic)
     const int V = C >> 3;
     const int v = threadIdx.x % V;
@@ -100,6 +102,8 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, long long ldx, __h
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 long long pixels_per_stat, int C, int G, float eps, int silu,
                                 const float* __restrict__ partials, int nblk) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     extern __shared__ float sm[];  // mean[G], rstd[G]
     float* s_mean = sm;
     float* s_rstd = sm + G;
@@ -175,6 +179,8 @@ template <int kMaxVec>
 __global__ void layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int C,
                                  float eps) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -230,6 +236,8 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, long long ldx, __
 template <int kMaxVec>
 __global__ void row_stats_kernel(const __half* __restrict__ x, long long ldx, int rows, int C, float eps,
                                  float2* __restrict__ stats) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -279,11 +287,11 @@ extern "C" int tc_row_stats(const void* x, long long ldx, int rows, int C, float
     const __half* xp = reinterpret_cast<const __half*>(x);
     float2* sp = reinterpret_cast<float2*>(stats);
     if (C <= 512)
-        row_stats_kernel<2><<<blocks, threads, 0, stream>>>(xp, ldx, rows, C, eps, sp);
+        tc_host::launch(row_stats_kernel<2>, dim3(blocks), dim3(threads), 0, stream, 1, xp, ldx, rows, C, eps, sp);
     else if (C <= 1280)
-        row_stats_kernel<5><<<blocks, threads, 0, stream>>>(xp, ldx, rows, C, eps, sp);
+        tc_host::launch(row_stats_kernel<5>, dim3(blocks), dim3(threads), 0, stream, 1, xp, ldx, rows, C, eps, sp);
     else
-        row_stats_kernel<8><<<blocks, threads, 0, stream>>>(xp, ldx, rows, C, eps, sp);
+        tc_host::launch(row_stats_kernel<8>, dim3(blocks), dim3(threads), 0, stream, 1, xp, ldx, rows, C, eps, sp);
     count_launch();
     TC_CHECK_LAUNCH("row_stats_kernel");
     return TC_OK;
@@ -314,7 +322,7 @@ extern "C" int tc_groupnorm(const void* x, long long ldx, void* y, long long ldy
     if (cap < 1) cap = 1;
     if (cap > kGnMaxPartials) cap = kGnMaxPartials;
     if (nblk > cap) nblk = cap;
-    gn_stats_kernel<<<dim3(nblk, n_stat), threads, (size_t)k * 2 * C * sizeof(float), stream>>>(
+    tc_host::launch(gn_stats_kernel, dim3(dim3(nblk, n_stat)), dim3(threads), (size_t)k * 2 * C * sizeof(float), stream, 1, 
         reinterpret_cast<const __half*>(x), ldx, pps, C, G, ws);
     count_launch();
     TC_CHECK_LAUNCH("gn_stats_kernel");
@@ -324,7 +332,7 @@ extern "C" int tc_groupnorm(const void* x, long long ldx, void* y, long long ldy
     int cap2 = (2 * sm_count()) / n_stat;
     if (cap2 < 1) cap2 = 1;
     if (nblk2 > cap2) nblk2 = cap2;
-    gn_apply_kernel<<<dim3(nblk2, n_stat), threads, 2 * G * sizeof(float), stream>>>(
+    tc_host::launch(gn_apply_kernel, dim3(dim3(nblk2, n_stat)), dim3(threads), 2 * G * sizeof(float), stream, 1, 
         reinterpret_cast<const __half*>(x), ldx, reinterpret_cast<__half*>(y), ldy, gamma, beta, pps, C, G, eps, silu,
         ws, nblk);
     count_launch();
@@ -344,11 +352,11 @@ extern "C" int tc_layernorm(const void* x, long long ldx, void* y, long long ldy
     const __half* xp = reinterpret_cast<const __half*>(x);
     __half* yp = reinterpret_cast<__half*>(y);
     if (C <= 512)
-        layernorm_kernel<2><<<blocks, threads, 0, stream>>>(xp, ldx, yp, ldy, gamma, beta, rows, C, eps);
+        tc_host::launch(layernorm_kernel<2>, dim3(blocks), dim3(threads), 0, stream, 1, xp, ldx, yp, ldy, gamma, beta, rows, C, eps);
     else if (C <= 1280)
-        layernorm_kernel<5><<<blocks, threads, 0, stream>>>(xp, ldx, yp, ldy, gamma, beta, rows, C, eps);
+        tc_host::launch(layernorm_kernel<5>, dim3(blocks), dim3(threads), 0, stream, 1, xp, ldx, yp, ldy, gamma, beta, rows, C, eps);
     else
-        layernorm_kernel<8><<<blocks, threads, 0, stream>>>(xp, ldx, yp, ldy, gamma, beta, rows, C, eps);
+        tc_host::launch(layernorm_kernel<8>, dim3(blocks), dim3(threads), 0, stream, 1, xp, ldx, yp, ldy, gamma, beta, rows, C, eps);
     count_launch();
     TC_CHECK_LAUNCH("layernorm_kernel");
     return TC_OK;
