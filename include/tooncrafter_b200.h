@@ -49,7 +49,7 @@ int tc_sm_count(void);
  * with m = (n*oH + y)*oW + x over the output pixel grid [oN][oH][oW]; A reads outside [a_N][a_H][a_W]
  * are zero (TMA out-of-bounds fill == the conv's zero padding).
  * epilogue: a = ln_stats ? rstd_m*(acc - mean_m*ln_u[j]) : acc;  v = a + bias[j] + bias2[m / bias2_rows_per][j];
- *           v = v*acc_scale + res[m][j];  (GEGLU optional)
+ *           v = v*acc_scale + res[m][j];  (GEGLU optional; optional per-row {sum, sumsq} of the outputs)
  *
  * Replaces (reference call sites): nn.Conv2d 3x3 / 1x1 (openaimodel3d.py:68,96,154,179,187,386,545;
  * autoencoder_dualref.py:52-69,914-935), nn.Conv3d (3,1,1) (openaimodel3d.py:255-266; autoencoder_dualref.py
@@ -86,8 +86,18 @@ typedef struct {
   /* folded LayerNorm of the A operand (attention.py:225-227,243-245): with Wt pre-multiplied by gamma,
    * LN(x) @ W^T = rstd_m * (acc - mean_m * ln_u[j]) (+ bias' = beta @ W^T + b).  ln_stats = {mean, rstd} per output
    * row from tc_row_stats, ln_u[j] = sum_k Wt[j][k].  Both NULL for plain layers. */
-  const float* ln_stats; /* [M][2] */
+  const float* ln_stats; /* [M][2], or with ln_nslots > 0: [M][ln_nslots][2] partial {sum, sum of squares} */
   const float* ln_u;     /* [n_cols] */
+  /* ln_nslots > 0: ln_stats holds the partial row sums a producer GEMM wrote through row_stats (below); the epilogue
+   * finishes them itself: mean = S1/C, rstd = rsqrt(S2/C - mean^2 + ln_eps) with C = a_C (taps must be 1). */
+  int ln_nslots;
+  float ln_eps;
+  /* producer side: per output row, {sum, sum of squares} of the fp16-rounded outputs this launch writes, one slot per
+   * N tile: slot = j / block_n, [M][row_stats_slots][2] floats, where row_stats_slots must equal
+   * ceil(n_cols/block_n) (so block_n must be given).  Feeds the LayerNorm fold of the consumer without a
+   * separate statistics pass over the activation.  NULL = off. */
+  float* row_stats;
+  int row_stats_slots;
 } TcConvGemm;
 
 int tc_conv_gemm(const TcConvGemm* desc, void* stream);

@@ -25,7 +25,8 @@ def _view2d(t, rows, cols, ld, off):
 
 def conv_gemm(a, a_dims, a_strides, w, taps, out, out_dims, n_cols, *, ldc=None, bias=None, bias2=None,
               bias2_rows_per=0, res=None, ldr=None, acc_scale=1.0, geglu=False, block_n=0, a_offset=0,
-              out_offset=0, res_offset=0, ln_stats=None, ln_u=None):
+              out_offset=0, res_offset=0, ln_stats=None, ln_u=None, ln_nslots=0, ln_eps=1e-5, row_stats=None,
+              row_stats_slots=0):
     aN, aH, aW, C = a_dims
     sN, sH, sW = a_strides
     A = _strided(a, (aN, aH, aW, C), (sN, sH, sW, 1), a_offset).float()
@@ -44,7 +45,13 @@ def conv_gemm(a, a_dims, a_strides, w, taps, out, out_dims, n_cols, *, ldc=None,
     assert w.shape[1] == len(taps) * C, f"weight K {w.shape[1]} != taps*C {len(taps) * C}"
     assert n_cols <= w.shape[0]
     acc = X @ w[:n_cols].float().t()
-    if ln_stats is not None:
+    if ln_stats is not None and ln_nslots > 0:
+        # partial {sum, sumsq} slots written by a producer launch (any slot layout: only the totals matter)
+        ps = ln_stats.view(-1)[:M * ln_nslots * 2].view(M, ln_nslots, 2).float().sum(1)
+        mean = ps[:, 0:1] / C
+        rstd = torch.rsqrt((ps[:, 1:2] / C - mean * mean).clamp_min(0) + ln_eps)
+        acc = rstd * (acc - mean * ln_u[:n_cols].float())
+    elif ln_stats is not None:
         st = ln_stats.view(-1, 2)[:M].float()
         acc = st[:, 1:2] * (acc - st[:, 0:1] * ln_u[:n_cols].float())
     if bias is not None:
@@ -65,6 +72,13 @@ def conv_gemm(a, a_dims, a_strides, w, taps, out, out_dims, n_cols, *, ldc=None,
         val, width = acc, n_cols
     ldc = ldc if ldc is not None else width
     _view2d(out, M, width, ldc, out_offset).copy_(val.half())
+    if row_stats is not None:
+        assert block_n > 0 and row_stats_slots == -(-n_cols // block_n) and not geglu
+        q = val.half().float()
+        rs = row_stats.view(-1)[:M * row_stats_slots * 2].view(M, row_stats_slots, 2)
+        rs.zero_()
+        rs[:, 0, 0] = q.sum(1)
+        rs[:, 0, 1] = (q * q).sum(1)
 
 
 def groupnorm(x, y, gamma, beta, *, frames, frames_per_stat, hw, C, G=32, eps=1e-5, silu=False, ldx=None, ldy=None,

@@ -136,6 +136,40 @@ def test_linear_with_folded_layernorm(ops, rows, C, N, geglu):
     _close(out, ref, "linear with folded LayerNorm", rel=4e-3, abs_=2e-3)
 
 
+@pytest.mark.parametrize("rows,C,bn,N2,geglu", [(4196, 320, 160, 960, False), (1000, 640, 160, 640, False),
+                                                 (3000, 1280, 256, 2560, True), (70000, 320, 160, 320, False)])
+def test_row_stats_from_producer_epilogue(ops, rows, C, bn, N2, geglu):
+    """The GEMM that writes an activation also writes per-row {sum, sumsq} partials of its fp16 outputs; the consuming
+    LayerNorm-folded GEMM finishes them in its epilogue  ==  Linear(LayerNorm(Linear(x) + res))."""
+    from tooncrafter_b200 import engine
+    x0 = _rand(rows, C, seed=81).half()
+    w0 = _rand(C, C, scale=C ** -0.5, seed=82).half()
+    b0 = _rand(C, seed=83).float()
+    res = (_rand(rows, C, seed=84) * 2 + 0.5).half()
+    slots = -(-C // bn)
+    mid = torch.zeros(rows, C, dtype=torch.float16, device=DEV)
+    part = torch.full((rows, slots, 2), float("nan"), device=DEV)
+    ops.linear(x0, w0, mid, rows=rows, K=C, n_cols=C, bias=b0, res=res, block_n=bn, row_stats=part, row_stats_slots=slots)
+    _close(mid, x0.float() @ w0.float().t() + b0 + res.float(), "producer output")
+    tot = part.sum(1)
+    m32 = mid.float()
+    assert (tot[:, 0] - m32.sum(1)).abs().max().item() <= 2e-3 * m32.abs().sum(1).max().item() / 10 + 1e-3
+    assert ((tot[:, 1] - (m32 * m32).sum(1)).abs() / (m32 * m32).sum(1)).max().item() < 1e-5
+    ln = torch.nn.LayerNorm(C).to(DEV)
+    with torch.no_grad():
+        ln.weight.copy_(_rand(C, seed=85) * 0.2 + 1.0)
+        ln.bias.copy_(_rand(C, seed=86) * 0.2)
+    w = _rand(N2, C, scale=C ** -0.5, seed=87)
+    b = _rand(N2, seed=88)
+    f = engine.fold_layernorm(w, b, ln, torch.device(DEV), perm=engine.geglu_perm(N2).to(DEV) if geglu else None)
+    out = torch.zeros(rows, N2 // 2 if geglu else N2, dtype=torch.float16, device=DEV)
+    ops.linear(mid, f.w, out, rows=rows, K=C, n_cols=N2, bias=f.c, ln_stats=part, ln_u=f.u, ln_nslots=slots, ln_eps=1e-5,
+               geglu=geglu, block_n=256 if geglu else 0)
+    h = F.linear(F.layer_norm(m32, (C,), ln.weight, ln.bias, 1e-5), w, b)
+    ref = h[:, :N2 // 2] * F.gelu(h[:, N2 // 2:]) if geglu else h
+    _close(out, ref, "consumer of producer-side row statistics", rel=4e-3, abs_=2e-3)
+
+
 @pytest.mark.parametrize("N,H,W,Cin,Cout", [(4, 20, 32, 128, 192), (6, 5, 8, 256, 320), (2, 40, 64, 64, 320),
                                              (3, 10, 16, 320, 4), (1, 16, 256, 128, 128)])
 def test_conv3x3(ops, N, H, W, Cin, Cout):

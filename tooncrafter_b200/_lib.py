@@ -42,6 +42,10 @@ class TcConvGemm(C.Structure):
         ("block_n", C.c_int),
         ("ln_stats", C.c_void_p),
         ("ln_u", C.c_void_p),
+        ("ln_nslots", C.c_int),
+        ("ln_eps", C.c_float),
+        ("row_stats", C.c_void_p),
+        ("row_stats_slots", C.c_int),
     ]
 
 

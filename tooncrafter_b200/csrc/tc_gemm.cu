@@ -35,6 +35,10 @@ struct alignas(64) GemmKParams {
     int tma_store;     // epilogue writes through shared memory + TMA stores (whole 32-column chunks)
     CUtensorMap tmOw;  // output, per-warp box {32 cols, wbW, wbH, wbN} (warp_box != 0)
     int warp_box;      // each epilogue warp's 32 rows form a box: per-warp TMA stores, no 128-thread barriers
+    float2* row_stats; // producer: per-row {sum, sumsq} partials, [M][row_stats_slots]
+    int row_stats_slots;
+    int ln_nslots;     // consumer: ln_stats holds [M][ln_nslots] partial sums, finished in the epilogue
+    float ln_eps, ln_inv_c;
     int b_resident;    // the whole K extent of one B (weight) N-tile stays in shared memory across M tiles
     int taps;
     int tap_dx[TC_MAX_TAPS], tap_dy[TC_MAX_TAPS], tap_dn[TC_MAX_TAPS];
@@ -135,6 +139,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_epi + 1024) + 1023) & ~uintptr_t(1023));
     // 64 x 64 identity (K-major, 128B-swizzled like a weight tile): the B operand of the residual k-blocks
     uint8_t* s_eye = s_stage + 16384;
+    // producer-side row statistics: column group 1 hands its partials to group 0 (two buffers by tile parity)
+    float2* s_rs = reinterpret_cast<float2*>(s_eye + 8192);
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&p.tmA);
@@ -397,9 +403,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 
             float ln_mean = 0.f, ln_rstd = 1.f;
             if (p.ln_stats && row_ok) {
-                const float2 st = __ldg(p.ln_stats + m);
-                ln_mean = st.x;
-                ln_rstd = st.y;
+                if (p.ln_nslots > 0) {
+                    // partial {sum, sumsq} slots written by the producer GEMM's epilogue (fixed order: deterministic)
+                    float s1 = 0.f, s2 = 0.f;
+                    const float2* ps = p.ln_stats + m * p.ln_nslots;
+#pragma unroll 4
+                    for (int i = 0; i < p.ln_nslots; ++i) {
+                        const float2 st = __ldg(ps + i);
+                        s1 += st.x;
+                        s2 += st.y;
+                    }
+                    ln_mean = s1 * p.ln_inv_c;
+                    const float var = fmaxf(s2 * p.ln_inv_c - ln_mean * ln_mean, 0.f);
+                    ln_rstd = rsqrtf(var + p.ln_eps);
+                } else {
+                    const float2 st = __ldg(p.ln_stats + m);
+                    ln_mean = st.x;
+                    ln_rstd = st.y;
+                }
             }
             // ---- residual prefetch (up to 128 columns = 16 x 16 B per thread)
             uint4 rres[16];
@@ -448,6 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
                 const int dbg = g_tc_gemm_debug;
                 uint32_t r[32];
+                float rs_sum = 0.f, rs_sq = 0.f;
                 if (kEpi == 0 && cg * 32 < width) tc::tmem_ld32(taddr + (uint32_t)(cg * 32), r);
 #pragma unroll 1
                 for (int jc = 0; jc < 4; ++jc) {
@@ -521,6 +543,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                         }
                         // next chunk's accumulator read flies while this one is staged and stored
                         if (c + 64 < width) tc::tmem_ld32(taddr + (uint32_t)(c + 64), r);
+                        if (p.row_stats) {
+                            // statistics of the values the consumer will read: the fp16-rounded outputs
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pk[i]));
+                                rs_sum += f.x + f.y;
+                                rs_sq = fmaf(f.x, f.x, fmaf(f.y, f.y, rs_sq));
+                            }
+                        }
                     } else {
                         // weight rows of this N tile are [value half (BN/2) | gate half (BN/2)]
 #pragma unroll
@@ -589,6 +620,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                             tc::tma_store_4d(stg, &p.tmO, nt * width + c, x0, y0, n0);
                             tc::bulk_commit_group();
                         }
+                    }
+                }
+                if (kEpi == 0 && p.row_stats) {
+                    // one slot per N tile: group 1 hands {sum, sumsq} of its columns to the warp of group 0 that owns
+                    // the same rows (64-thread named barrier, group 1 only arrives).  Group 1 may run one tile ahead of
+                    // group 0 (two TMEM accumulators), so buffers AND barrier ids alternate with the tile parity: two
+                    // arrivals of the same warp on one id would complete the barrier without group 0.
+                    float2* hand = s_rs + (ti & 1) * 128 + row;
+                    const int bar_id = 4 + q + 4 * (ti & 1);
+                    if (cg == 1) {
+                        *hand = make_float2(rs_sum, rs_sq);
+                        asm volatile("bar.arrive %0, 64;" ::"r"(bar_id) : "memory");
+                    } else {
+                        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+                        const float2 o = *hand;
+                        if (row_ok) p.row_stats[m * p.row_stats_slots + nt] = make_float2(rs_sum + o.x, rs_sq + o.y);
                     }
                 }
             } else if (!geglu) {
@@ -813,6 +860,11 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
                  "tc_conv_gemm: strides must be multiples of 8 elements");
     TC_CHECK_ARG((d->ln_stats == nullptr) == (d->ln_u == nullptr), "tc_conv_gemm: ln_stats and ln_u go together");
     TC_CHECK_ARG(!d->ln_stats || d->n_cols % 16 == 0, "tc_conv_gemm: folded LayerNorm needs n_cols % 16 == 0");
+    TC_CHECK_ARG(!d->ln_stats || d->ln_nslots == 0 || (d->ln_nslots > 0 && d->ln_nslots <= 64 && d->taps == 1),
+                 "tc_conv_gemm: partial-sum LayerNorm statistics need taps == 1 and 1..64 slots");
+    TC_CHECK_ARG(!d->row_stats || (d->block_n > 0 && !(d->flags & TC_EPI_GEGLU) &&
+                                   d->row_stats_slots == (d->n_cols + d->block_n - 1) / d->block_n),
+                 "tc_conv_gemm: row_stats needs an explicit block_n and row_stats_slots == ceil(n_cols/block_n)");
     TC_CHECK_ARG(!d->res || (d->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(d->res) & 15) == 0),
                  "tc_conv_gemm: residual must be 16-byte aligned");
     const bool geglu = (d->flags & TC_EPI_GEGLU) != 0;
@@ -886,6 +938,11 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
     p.flags = d->flags;
     p.ln_stats = reinterpret_cast<const float2*>(d->ln_stats);
     p.ln_u = d->ln_u;
+    p.ln_nslots = d->ln_stats ? d->ln_nslots : 0;
+    p.ln_eps = d->ln_eps;
+    p.ln_inv_c = 1.0f / (float)d->a_C;
+    p.row_stats = reinterpret_cast<float2*>(d->row_stats);
+    p.row_stats_slots = d->row_stats_slots;
 
     // --- tensor maps
     {
@@ -954,8 +1011,8 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
         }
     }
     const int stage_bytes = kAStageBytes + (pair ? BN / 2 : BN) * 128;
-    // alignment slack, barriers, epilogue vectors, store staging, identity tile
-    const int kFixedSmem = 1024 + 512 + 4096 + 1024 + 16384 + 8192;
+    // alignment slack, barriers, epilogue vectors, store staging, identity tile, row-statistics hand-over
+    const int kFixedSmem = 1024 + 512 + 4096 + 1024 + 16384 + 8192 + 2048;
     const int smem_budget = 227 * 1024 - kFixedSmem;
     int stages = smem_budget / stage_bytes;
     if (stages > 8) stages = 8;
@@ -977,6 +1034,7 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
                                             : (size_t)stages * stage_bytes) + kFixedSmem;
 
     const int epi = !p.tma_store ? 2 : (geglu ? 1 : 0);
+    if (p.row_stats && epi != 0) return fail(TC_ERR_INVALID, "tc_conv_gemm: row_stats needs the TMA-store epilogue (n_cols % 16 == 0, block_n % 32 == 0)");
     using KernelFn = void (*)(GemmKParams);
     static const KernelFn kernels[2][3] = {
         {tc_gemm_kernel<false, 0>, tc_gemm_kernel<false, 1>, tc_gemm_kernel<false, 2>},

@@ -18,6 +18,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -108,7 +110,8 @@ def pack_transformer_block(tb, dev, cross: bool):
 # ------------------------------------------------------------------------------------------------ shared builders
 def gemm(bld: Builder, a: Act, w: torch.Tensor, taps, out: Act, *, a_dims=None, a_strides=None, out_dims=None,
          bias=None, bias2=None, bias2_rows_per=0, res: Optional[Act] = None, acc_scale=1.0, geglu=False,
-         n_cols=None, block_n=0, ln_stats=None, ln_u=None):
+         n_cols=None, block_n=0, ln_stats=None, ln_u=None, ln_nslots=0, ln_eps=1e-5, row_stats=None,
+         row_stats_slots=0):
     """Record one tc_conv_gemm launch: out = epilogue(im2col(a) @ w.T)."""
     if a_dims is None:
         a_dims = (a.N, a.H, a.W, a.C)
@@ -119,7 +122,8 @@ def gemm(bld: Builder, a: Act, w: torch.Tensor, taps, out: Act, *, a_dims=None, 
     bld.op(ops.conv_gemm, a.t, a_dims, a_strides, w, taps, out.t, out_dims, n_cols, ldc=out.ld, bias=bias,
            bias2=bias2, bias2_rows_per=bias2_rows_per, res=None if res is None else res.t,
            ldr=None if res is None else res.ld, acc_scale=acc_scale, geglu=geglu, block_n=block_n, a_offset=a.off,
-           out_offset=out.off, res_offset=0 if res is None else res.off, ln_stats=ln_stats, ln_u=ln_u)
+           out_offset=out.off, res_offset=0 if res is None else res.off, ln_stats=ln_stats, ln_u=ln_u,
+           ln_nslots=ln_nslots, ln_eps=ln_eps, row_stats=row_stats, row_stats_slots=row_stats_slots)
 
 
 def linear(bld: Builder, a: Act, w, out: Act, **kw):
@@ -141,20 +145,44 @@ def groupnorm(bld: Builder, x: Act, y: Act, n: _P, *, frames_per_stat=1, silu=Fa
            eps=n.eps if eps is None else eps, silu=silu, ldx=x.ld, ldy=y.ld, x_offset=x.off, y_offset=y.off)
 
 
-def ln_linear(bld: Builder, x: Act, f: _P, out: Act, **kw):
-    """out = LN(x) @ W^T (+ ...) with the LayerNorm folded into the GEMM epilogue: one statistics pass over x
-    (tc_row_stats) replaces the LayerNorm kernel and its normalised fp16 copy of x."""
+class RowStats:
+    """Partial LayerNorm statistics of an activation, written by the epilogue of the GEMM that produces it
+    ([rows][slots] {sum, sumsq}; tc_conv_gemm row_stats) and finished by the epilogue of the GEMM that consumes it."""
+
+    def __init__(self, bld: Builder, rows: int, width: int):
+        self.bn = 160 if width in (320, 640) else (256 if width % 256 == 0 else 0)   # producer tile (fixes the slot count)
+        if os.environ.get("TC_ENGINE_ROWSTATS") == "0":                             # A/B: separate tc_row_stats passes
+            self.bn = 0
+        self.slots = -(-width // self.bn) if self.bn else 0
+        self.bld = bld
+        self.buf, self.off = bld.raw(2 * self.slots * rows, torch.float32) if self.bn else (None, None)
+
+    def producer_kw(self):
+        return dict(block_n=self.bn, row_stats=self.buf, row_stats_slots=self.slots) if self.bn else {}
+
+    def free(self):
+        if self.bn:
+            self.bld.free_raw(self.off)
+
+
+def ln_linear(bld: Builder, x: Act, f: _P, out: Act, stats: Optional[RowStats] = None, **kw):
+    """out = LN(x) @ W^T (+ ...) with the LayerNorm folded into the GEMM epilogue.  The row statistics come from the
+    producer of x (`stats`, no extra pass over x) or from one tc_row_stats pass; either way the LayerNorm kernel and
+    its normalised fp16 copy of x are gone."""
     assert x.off == 0
-    stats, off = bld.raw(2 * x.rows, torch.float32)
-    bld.op(ops.row_stats, x.t, stats, rows=x.rows, C=x.C, eps=f.eps, ldx=x.ld)
-    linear(bld, x, f.w, out, bias=f.c, ln_stats=stats, ln_u=f.u, **kw)
+    if stats is not None and stats.bn:
+        linear(bld, x, f.w, out, bias=f.c, ln_stats=stats.buf, ln_u=f.u, ln_nslots=stats.slots, ln_eps=f.eps, **kw)
+        return
+    buf, off = bld.raw(2 * x.rows, torch.float32)
+    bld.op(ops.row_stats, x.t, buf, rows=x.rows, C=x.C, eps=f.eps, ldx=x.ld)
+    linear(bld, x, f.w, out, bias=f.c, ln_stats=buf, ln_u=f.u, **kw)
     bld.free_raw(off)
 
 
-def feed_forward(bld: Builder, x: Act, p: _P, out: Act):
+def feed_forward(bld: Builder, x: Act, p: _P, out: Act, stats: Optional[RowStats] = None):
     """x + W2 (a * gelu(g)), with (a, g) = W1 LN(x)   (attention.py:245, 415-442)."""
     hid = bld.act(x.N, x.H, x.W, 4 * x.C)
-    ln_linear(bld, x, p.ff1, hid, geglu=True, block_n=GEGLU_BN)
+    ln_linear(bld, x, p.ff1, hid, stats=stats, geglu=True, block_n=GEGLU_BN)
     linear(bld, hid, p.ff2_w, out, bias=p.ff2_b, res=x)
     hid.free()
 
@@ -300,20 +328,20 @@ class UNetEngine:
             cur = nxt
         h2.free()
 
-    def _self_attn_spatial(self, bld, x: Act, tb: _P, heads: int, out: Act):
+    def _self_attn_spatial(self, bld, x: Act, tb: _P, heads: int, out: Act, s_in: RowStats, s_out: RowStats):
         qkv = bld.act(x.N, x.H, x.W, 3 * x.C)
-        ln_linear(bld, x, tb.qkv1, qkv)
+        ln_linear(bld, x, tb.qkv1, qkv, stats=s_in)
         att = bld.act(x.N, x.H, x.W, x.C)
         L, C = x.H * x.W, x.C
         bld.op(ops.attention, qkv.t, [dict(k=qkv.t, v=qkv.t, ldk=3 * C, ldv=3 * C, Lk=L, k_offset=C, v_offset=2 * C)],
                att.t, q_batches=x.N, Lq=L, heads=heads, scale=64 ** -0.5, ldq=3 * C, ldo=C)
         qkv.free()
-        linear(bld, att, tb.o1_w, out, bias=tb.o1_b, res=x)
+        linear(bld, att, tb.o1_w, out, bias=tb.o1_b, res=x, **s_out.producer_kw())
         att.free()
 
-    def _cross_attn(self, bld, x: Act, tb: _P, heads: int, out: Act, kv, st):
+    def _cross_attn(self, bld, x: Act, tb: _P, heads: int, out: Act, kv, st, s_in: RowStats, s_out: RowStats):
         q = bld.act(x.N, x.H, x.W, x.C)
-        ln_linear(bld, x, tb.q2, q)
+        ln_linear(bld, x, tb.q2, q, stats=s_in)
         att = bld.act(x.N, x.H, x.W, x.C)
         L, C, T = x.H * x.W, x.C, st["T"]
         segs = [dict(k=kv["txt"], v=kv["txt"], ldk=2 * C, ldv=2 * C, Lk=kv["n_txt"], kv_div=T, v_offset=C)]
@@ -321,56 +349,66 @@ class UNetEngine:
             segs.append(dict(k=kv["img"], v=kv["img"], ldk=2 * C, ldv=2 * C, Lk=kv["n_img"], kv_div=1, v_offset=C))
         bld.op(ops.attention, q.t, segs, att.t, q_batches=x.N, Lq=L, heads=heads, scale=64 ** -0.5, ldq=C, ldo=C)
         q.free()
-        linear(bld, att, tb.o2_w, out, bias=tb.o2_b, res=x)
+        linear(bld, att, tb.o2_w, out, bias=tb.o2_b, res=x, **s_out.producer_kw())
         att.free()
 
     def _spatial_tf(self, bld: Builder, p: _P, x: Act, dst: Act, st, kv) -> None:
         N, H, W = x.N, x.H, x.W
         n = bld.act(N, H, W, p.C)
         groupnorm(bld, x, n, p.norm)
+        # LayerNorm statistics of t0 / t1 / t2 ride the epilogues of the GEMMs that write them
+        rows = N * H * W
+        s0, s1, s2 = (RowStats(bld, rows, p.inner) for _ in range(3))
         t0 = bld.act(N, H, W, p.inner)
-        linear(bld, n, p.in_w, t0, bias=p.in_b)
+        linear(bld, n, p.in_w, t0, bias=p.in_b, **s0.producer_kw())
         n.free()
         t1 = bld.act(N, H, W, p.inner)
-        self._self_attn_spatial(bld, t0, p.tb, p.heads, t1)
+        self._self_attn_spatial(bld, t0, p.tb, p.heads, t1, s0, s1)
         t0.free()
         t2 = bld.act(N, H, W, p.inner)
-        self._cross_attn(bld, t1, p.tb, p.heads, t2, kv, st)
+        self._cross_attn(bld, t1, p.tb, p.heads, t2, kv, st, s1, s2)
         t1.free()
         t3 = bld.act(N, H, W, p.inner)
-        feed_forward(bld, t2, p.tb, t3)
+        feed_forward(bld, t2, p.tb, t3, stats=s2)
         t2.free()
+        for r in (s0, s1, s2):
+            r.free()
         linear(bld, t3, p.out_w, dst, bias=p.out_b, res=x)
         t3.free()
 
-    def _temporal_self_attn(self, bld, x: Act, fqkv: _P, wo, bo, heads: int, out: Act, st):
+    def _temporal_self_attn(self, bld, x: Act, fqkv: _P, wo, bo, heads: int, out: Act, st, s_in: RowStats,
+                            s_out: RowStats):
         qkv = bld.act(x.N, x.H, x.W, 3 * x.C)
-        ln_linear(bld, x, fqkv, qkv)
+        ln_linear(bld, x, fqkv, qkv, stats=s_in)
         att = bld.act(x.N, x.H, x.W, x.C)
         C = x.C
         bld.op(ops.temporal_attention, qkv.t, qkv.t, qkv.t, att.t, ld=3 * C, ldo=C, B=st["B"], T=st["T"], P=x.H * x.W,
                heads=heads, scale=64 ** -0.5, k_offset=C, v_offset=2 * C)
         qkv.free()
-        linear(bld, att, wo, out, bias=bo, res=x)
+        linear(bld, att, wo, out, bias=bo, res=x, **s_out.producer_kw())
         att.free()
 
     def _temporal_tf(self, bld: Builder, p: _P, x: Act, dst: Act, st) -> None:
         N, H, W = x.N, x.H, x.W
         n = bld.act(N, H, W, p.C)
         groupnorm(bld, x, n, p.norm, frames_per_stat=st["T"])
+        rows = N * H * W
+        s0, s1, s2 = (RowStats(bld, rows, p.inner) for _ in range(3))
         t0 = bld.act(N, H, W, p.inner)
-        linear(bld, n, p.in_w, t0, bias=p.in_b)
+        linear(bld, n, p.in_w, t0, bias=p.in_b, **s0.producer_kw())
         n.free()
         tb = p.tb
         t1 = bld.act(N, H, W, p.inner)
-        self._temporal_self_attn(bld, t0, tb.qkv1, tb.o1_w, tb.o1_b, p.heads, t1, st)
+        self._temporal_self_attn(bld, t0, tb.qkv1, tb.o1_w, tb.o1_b, p.heads, t1, st, s0, s1)
         t0.free()
         t2 = bld.act(N, H, W, p.inner)
-        self._temporal_self_attn(bld, t1, tb.qkv2, tb.o2_w, tb.o2_b, p.heads, t2, st)
+        self._temporal_self_attn(bld, t1, tb.qkv2, tb.o2_w, tb.o2_b, p.heads, t2, st, s1, s2)
         t1.free()
         t3 = bld.act(N, H, W, p.inner)
-        feed_forward(bld, t2, tb, t3)
+        feed_forward(bld, t2, tb, t3, stats=s2)
         t2.free()
+        for r in (s0, s1, s2):
+            r.free()
         linear(bld, t3, p.out_w, dst, bias=p.out_b, res=x)
         t3.free()
 

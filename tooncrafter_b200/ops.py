@@ -55,10 +55,14 @@ def conv_gemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, taps: Sequenc
               bias2: Optional[torch.Tensor] = None, bias2_rows_per: int = 0, res: Optional[torch.Tensor] = None,
               ldr: Optional[int] = None, acc_scale: float = 1.0, geglu: bool = False, block_n: int = 0,
               a_offset: int = 0, out_offset: int = 0, res_offset: int = 0,
-              ln_stats: Optional[torch.Tensor] = None, ln_u: Optional[torch.Tensor] = None) -> None:
+              ln_stats: Optional[torch.Tensor] = None, ln_u: Optional[torch.Tensor] = None,
+              ln_nslots: int = 0, ln_eps: float = 1e-5, row_stats: Optional[torch.Tensor] = None,
+              row_stats_slots: int = 0) -> None:
     """out = epilogue(im2col(a) @ w.T).  a_dims = (N, H, W, C), a_strides = (sN, sH, sW) in elements.
 
     `*_offset` are element offsets applied to the base pointers (channel-slice views).
+    ln_nslots > 0: `ln_stats` holds [M][ln_nslots][2] partial row sums written by a producer launch (`row_stats=`,
+    `row_stats_slots = ceil(n_cols / block_n)`) instead of finished {mean, rstd} pairs.
     """
     _req_half(a, "a"); _req_half(w, "w"); _req_half(out, "out")
     lib = _lib.load()
@@ -95,6 +99,13 @@ def conv_gemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, taps: Sequenc
     if ln_stats is not None:
         d.ln_stats = ln_stats.data_ptr()
         d.ln_u = ln_u.data_ptr()
+        d.ln_nslots = ln_nslots
+        d.ln_eps = ln_eps
+    if row_stats is not None:
+        if row_stats.dtype != torch.float32:
+            raise TypeError("row_stats must be float32")
+        d.row_stats = row_stats.data_ptr()
+        d.row_stats_slots = row_stats_slots
     check(lib.tc_conv_gemm(C.byref(d), _stream()), "tc_conv_gemm")
 
 
