@@ -80,19 +80,19 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ldx, lon
         mine[C + v * 8 + i] = sq[i];
     }
     __syncthreads();
+    // block reduction in a fixed order (deterministic), one warp per (group, sum | sumsq) task: 32 threads walking
+    // rows_per_iter x cpg values serially cost ~3.7 us per launch, most of a small tensor's GroupNorm
     const int cpg = C / G;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-        float a = 0.f, b = 0.f;
-        for (int r = 0; r < rows_per_iter; ++r) {
-            const float* src = sm + (long long)r * 2 * C;
-            for (int c = 0; c < cpg; ++c) {
-                a += src[g * cpg + c];
-                b += src[C + g * cpg + c];
-            }
-        }
-        float* dst = partials + (((long long)s * gridDim.x + blockIdx.x) * G + g) * 2;
-        dst[0] = a;
-        dst[1] = b;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int n = rows_per_iter * cpg;
+    for (int task = warp; task < 2 * G; task += nwarps) {
+        const int g = task >> 1, which = task & 1;
+        const float* src = sm + which * C + g * cpg;
+        float a = 0.f;
+        for (int e = lane; e < n; e += 32) a += src[(long long)(e / cpg) * 2 * C + (e % cpg)];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) partials[(((long long)s * gridDim.x + blockIdx.x) * G + g) * 2 + which] = a;
     }
 }
 
@@ -110,19 +110,21 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, long long ldx, __h
     const int s = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int cpg = C / G;
-    for (int g = warp; g < G; g += nwarps) {
+    // 8 lanes per group: all groups of a 32-group layer are finished in one round by 8+ warps
+    for (int gb = warp * 4; gb < G; gb += nwarps * 4) {     // warp-uniform trip count: the shuffles use the full mask
+        const int g = gb + (lane >> 3);
         double a = 0.0, b = 0.0;
-        for (int k = lane; k < nblk; k += 32) {
+        for (int k = lane & 7; k < nblk && g < G; k += 8) {
             const float* src = partials + (((long long)s * nblk + k) * G + g) * 2;
             a += (double)src[0];
             b += (double)src[1];
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int o = 4; o > 0; o >>= 1) {
             a += __shfl_xor_sync(0xffffffffu, a, o);
             b += __shfl_xor_sync(0xffffffffu, b, o);
         }
-        if (lane == 0) {
+        if ((lane & 7) == 0 && g < G) {
             const double cnt = (double)pixels_per_stat * (double)cpg;
             const double mean = a / cnt;
             double var = b / cnt - mean * mean;
@@ -314,8 +316,9 @@ extern "C" int tc_groupnorm(const void* x, long long ldx, void* y, long long ldy
     int k = 512 / V;
     if (k < 1) k = 1;
     const int threads = V * k;
-    // each thread should see >= 8 pixels in the statistics pass; cap partial blocks per stat group
-    long long want = (pps + (long long)k * 16 - 1) / ((long long)k * 16);
+    // small tensors are latency-bound (a chain of dependent load rounds per thread): spread them over as many blocks as
+    // one round of 4 loads per thread allows; large ones are capped to one resident wave below
+    long long want = (pps + (long long)k * 4 - 1) / ((long long)k * 4);
     int nblk = (int)(want < 1 ? 1 : want);
     // exactly one resident wave (2 blocks of <= 512 threads per SM): 320 blocks on 296 slots ran as two waves
     int cap = (2 * sm_count()) / n_stat;
@@ -326,7 +329,7 @@ extern "C" int tc_groupnorm(const void* x, long long ldx, void* y, long long ldy
         reinterpret_cast<const __half*>(x), ldx, pps, C, G, ws);
     count_launch();
     TC_CHECK_LAUNCH("gn_stats_kernel");
-    long long want2 = (pps + (long long)k * 8 - 1) / ((long long)k * 8);
+    long long want2 = (pps + (long long)k * 4 - 1) / ((long long)k * 4);
     int nblk2 = (int)(want2 < 1 ? 1 : want2);
     // one wave as well: every block pays the fp64 finalize prologue once
     int cap2 = (2 * sm_count()) / n_stat;
