@@ -370,8 +370,7 @@ template <int kGroup>
 __global__ void temporal_attn_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
                                      const __half* __restrict__ v, long long ld, __half* __restrict__ out,
                                      long long ldo, int B, int T, int P, int heads, float scale_log2) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+    tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     constexpr int kItemsPerWarp = 32 / kGroup;
     constexpr int kWarps = 4;
     __shared__ __align__(16) __half sK[kWarps * kItemsPerWarp][kGroup][64];
@@ -486,8 +485,7 @@ __global__ void __launch_bounds__(128) temporal_attn_mma_kernel(const __half* __
                                                                 const __half* __restrict__ v, long long ld,
                                                                 __half* __restrict__ out, long long ldo, int B, int T,
                                                                 int P, int heads, float scale_log2) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+    tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     __shared__ __align__(128) uint8_t sV[4][16 * 128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t4 = lane & 3;
@@ -605,8 +603,7 @@ __global__ void __launch_bounds__(128) temporal_attn_mma_kernel(const __half* __
 
 // ===================================================================================== row softmax (in place)
 __global__ void softmax_rows_kernel(__half* __restrict__ s, long long lds, int rows, int cols, float scale_log2) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+    tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     const int row = blockIdx.x;
     if (row >= rows) return;
     __half* r = s + (long long)row * lds;

@@ -11,8 +11,7 @@ __device__ __forceinline__ void st16(void* p, const uint4& v) { *reinterpret_cas
 // ------------------------------------------------------------------------------------------------ layout
 __global__ void ncthw_to_cl_kernel(const float* __restrict__ x, __half* __restrict__ y, int B, int C, int T, int H,
                                    int W, int Cpad, int coff, float scale) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+    tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     const long long npix = (long long)B * T * H * W;
     const long long thw = (long long)T * H * W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
@@ -27,8 +26,7 @@ __global__ void ncthw_to_cl_kernel(const float* __restrict__ x, __half* __restri
 template <typename OutT>
 __global__ void cl_to_ncthw_kernel(const __half* __restrict__ x, long long ldx, OutT* __restrict__ y, int B, int C,
                                    int T, int H, int W) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+    tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     const long long npix = (long long)B * T * H * W;
     const long long thw = (long long)T * H * W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
@@ -46,8 +44,7 @@ __global__ void cl_to_ncthw_kernel(const __half* __restrict__ x, long long ldx, 
 }
 
 __global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restrict__ y, int N, int H, int W, int C) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+    tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     const int V = C >> 3;
     const long long total = (long long)N * (2 * H) * (2 * W) * V;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -66,8 +63,7 @@ __global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restri
 // y[ph][n][h2][w2][c] = x[n][2*h2 + (ph>>1)][2*w2 + (ph&1)][c]
 __global__ void phase_split2_kernel(const __half* __restrict__ x, __half* __restrict__ y, int N, int H, int W,
                                     int C) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+    tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     const int V = C >> 3;
     const int H2 = H >> 1, W2 = W >> 1;
     const long long total = (long long)4 * N * H2 * W2 * V;
@@ -88,8 +84,7 @@ __global__ void phase_split2_kernel(const __half* __restrict__ x, __half* __rest
 
 __global__ void copy2d_kernel(const __half* __restrict__ src, long long lds, __half* __restrict__ dst, long long ldd,
                               long long rows, int cols) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+    tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     const int V = cols >> 3;
     const long long total = rows * V;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -102,8 +97,7 @@ __global__ void copy2d_kernel(const __half* __restrict__ src, long long lds, __h
 
 __global__ void add2d_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
                              long long rows, int cols) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+    tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     const int V = cols >> 3;
     const long long total = rows * V;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -123,8 +117,7 @@ __global__ void add2d_kernel(const __half* __restrict__ x, long long ldx, __half
 // ------------------------------------------------------------------------------------------------ tiny linears
 // sinusoidal embedding: out[b][0:half] = cos(t*f_i), out[b][half:2*half] = sin(t*f_i), f_i = exp(-ln(1e4)*i/half)
 __global__ void sincos_kernel(const float* __restrict__ t, int B, int dim, float* __restrict__ out) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+    tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     const int half = dim / 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
@@ -141,8 +134,7 @@ template <typename OutT>
 __global__ void small_linear_kernel(const float* __restrict__ x, int B, int K, const __half* __restrict__ w,
                                     const float* __restrict__ bias, int J, OutT* __restrict__ y, long long ldy,
                                     int silu_in, int accumulate) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+    tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (j >= J) return;
@@ -205,8 +197,7 @@ __device__ __forceinline__ __half cfg_combine(__half ec, __half euc, float s) {
 // partial sums for std(e_c) and std(v): ws[b][blk][4] = {sum_ec, sumsq_ec, sum_v, sumsq_v} (double)
 __global__ void ddim_reduce_kernel(const __half* __restrict__ e_c, const __half* __restrict__ e_uc,
                                    const float* __restrict__ coef, long long n, double* __restrict__ ws) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+    tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     const int b = blockIdx.y;
     const float s = coef[0];
     const __half* ec = e_c + (long long)b * n;
@@ -249,8 +240,7 @@ __global__ void ddim_update_kernel(const __half* __restrict__ e_c, const __half*
                                    float* __restrict__ x_prev, float* __restrict__ pred_x0,
                                    const float* __restrict__ coef, long long n, const double* __restrict__ ws,
                                    int nblk) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+    tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     const int b = blockIdx.y;
     const float s = coef[0], phi = coef[1], sqrt_ac = coef[2], sqrt_1mac = coef[3], rescale = coef[4],
                 sqrt_aprev = coef[5], dir_coef = coef[6], sigma = coef[7];

@@ -38,8 +38,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // grid = (nblk, n_stat); block = V * k threads (V = C/8), thread t owns channel vector t % V.
 __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ldx, long long pixels_per_stat, int C, int G,
                                 float* __restrict__ partials) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+    tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     extern __shared__ float sm[];  // [rows_per_iter][2*C]: per-thread partials, reduced in a fixed order (deterministic)
     const int V = C >> 3;
     const int v = threadIdx.x % V;
@@ -102,8 +101,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, long long ldx, __h
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 long long pixels_per_stat, int C, int G, float eps, int silu,
                                 const float* __restrict__ partials, int nblk) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+    tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     extern __shared__ float sm[];  // mean[G], rstd[G]
     float* s_mean = sm;
     float* s_rstd = sm + G;
@@ -181,8 +179,7 @@ template <int kMaxVec>
 __global__ void layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int C,
                                  float eps) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+    tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -238,8 +235,7 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, long long ldx, __
 template <int kMaxVec>
 __global__ void row_stats_kernel(const __half* __restrict__ x, long long ldx, int rows, int C, float eps,
                                  float2* __restrict__ stats) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+    tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
