@@ -235,7 +235,12 @@ def test_conv3x3_stride2(ops):
 
 @pytest.mark.parametrize("frames,fps,hw,C,silu,eps", [(8, 1, 160, 320, True, 1e-5), (8, 4, 40, 1280, True, 1e-5),
                                                       (4, 1, 2560, 640, False, 1e-6), (16, 16, 640, 128, True, 1e-5),
-                                                      (2, 1, 20480, 256, True, 1e-6), (4, 2, 64, 1920, True, 1e-5)])
+                                                      (2, 1, 20480, 256, True, 1e-6), (4, 2, 64, 1920, True, 1e-5),
+                                                      # the UNet's shapes: group sizes 10 / 20 / 30 / 40 / 80 channels, ragged pixel counts
+                                                      (32, 16, 40, 1280, True, 1e-5), (32, 1, 160, 1280, True, 1e-5),
+                                                      (32, 16, 160, 1280, False, 1e-5), (8, 1, 2560, 320, True, 1e-5),
+                                                      (16, 1, 640, 640, True, 1e-5), (6, 1, 333, 960, True, 1e-5),
+                                                      (4, 2, 77, 2560, True, 1e-5), (16, 1, 2560, 512, True, 1e-6)])
 def test_groupnorm(ops, frames, fps, hw, C, silu, eps):
     x = (_rand(frames, hw, C, seed=41) * 1.5 + 0.3).half()
     gamma = (_rand(C, seed=42) * 0.2 + 1.0).float()
