@@ -182,6 +182,16 @@ def gemm_roofline(model, dev):
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm
+def gemm_traffic():
+    """(dram bytes per tc_gemm_kernel launch, provenance) from the committed ncu launch list, or (None, reason)."""
+    p = Path(__file__).resolve().parent / "profiles" / "r01_unet_b2_launches_final.gemm_traffic.json"
+    try:
+        d = json.loads(p.read_text())
+        return float(d["dram_bytes_per_launch"]), f"profiles/{p.name}: {d['launches']} launches, {d['source']}"
+    except Exception as e:      # noqa: BLE001 - the file is optional evidence, not a dependency of the measurement
+        return None, f"no ncu capture committed ({type(e).__name__})"
+
+
 def cpu_threads():
     """Host threads for the CPU arm: all cores up to 32 (beyond that the fp32 conv/GEMM mix of this UNet stops
     scaling and oversubscribed boxes get slower: 128 threads measured 185 s/forward vs 35 s on 8 dedicated cores)."""
@@ -365,7 +375,9 @@ def main():
         "clocks": clk,
         "roofline": {"bound": "tensor", "kernel": "tc_gemm_kernel (implicit-GEMM conv / linear, tcgen05)",
                      "achieved": roof["tflops"], "peak": peaks["tflops"], "unit": "TFLOP/s",
-                     "frac": roof["tflops"] / peaks["tflops"], "traffic": None, "peak_source": peaks["src"],
+                     "frac": roof["tflops"] / peaks["tflops"], "traffic": gemm_traffic()[0],
+                     "traffic_unit": "bytes of DRAM read+write per launch (ncu, average over the GEMM launches of one UNet forward)",
+                     "traffic_source": gemm_traffic()[1], "peak_source": peaks["src"],
                      "launches_per_unet_forward": roof["launches"], "avg_launch_us": roof["avg_launch_us"],
                      "flops_per_launch": roof["flops_per_launch"],
                      "share_of_unet_forward": roof["gemm_ms_per_forward"]},

@@ -69,7 +69,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
-    const int lane = tid & 31;
     const int q0 = blockIdx.x * 2 * kQTile;
     const int head = blockIdx.y;
     const int qb = blockIdx.z;

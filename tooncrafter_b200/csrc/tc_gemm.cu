@@ -67,8 +67,10 @@ struct alignas(64) GemmKParams {
 
 __device__ int g_tc_gemm_debug = 0;   // profiling aid (scripts/prof_epilogue.py): 1 = no global stores, 2 = no epilogue body,
                                       // 4 = record per-tile clock64() stamps of each warp role (scripts/trace_gemm.py)
+#if defined(TC_GEMM_TRACE) && TC_GEMM_TRACE
 constexpr int kTraceTiles = 32, kTraceSlots = 16, kTraceCtas = 160;
 __device__ unsigned long long g_tc_gemm_trace[kTraceCtas * kTraceTiles * kTraceSlots];
+#endif
 // compiled in only with -DTC_GEMM_TRACE=1 (python tooncrafter_b200/build.py --trace): even the disabled checks cost the
 // long-K convolutions 10-25 % (measured, scripts/ab_conv.py)
 #if defined(TC_GEMM_TRACE) && TC_GEMM_TRACE
@@ -380,7 +382,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         const int c_end = cg == 0 ? split : width;
         const bool vec_ok = (p.n_cols % 16) == 0;                   // all chunks complete -> 16-byte paths
         // TMA-store path: 32-column chunks, chunk k belongs to column group k & 1
-        constexpr bool tma_out = kEpi != 2;
         // staging: one 128-row box per column group, or (warp_box) one 32-row box per warp
         const bool warp_box = p.warp_box != 0;
         uint8_t* stg = warp_box ? s_stage + (warp - 2) * 2048 : s_stage + cg * 8192;
@@ -422,6 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     ln_rstd = st.y;
                 }
             }
+            const float ln_rm = -ln_rstd * ln_mean;
             // ---- residual prefetch (up to 128 columns = 16 x 16 B per thread)
             uint4 rres[16];
             if (kEpi == 2 && rrow && vec_ok) {
@@ -488,16 +490,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
                         if (p.ln_u) {
+                            // rstd*(acc - mean*u) + bias  ==  rstd*acc + (bias - rstd*mean*u): two FFMAs per value
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const float4 u4 = reinterpret_cast<const float4*>(su + c)[i];
-                                v[4 * i] = ln_rstd * (v[4 * i] - ln_mean * u4.x);
-                                v[4 * i + 1] = ln_rstd * (v[4 * i + 1] - ln_mean * u4.y);
-                                v[4 * i + 2] = ln_rstd * (v[4 * i + 2] - ln_mean * u4.z);
-                                v[4 * i + 3] = ln_rstd * (v[4 * i + 3] - ln_mean * u4.w);
+                                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (p.bias) b4 = reinterpret_cast<const float4*>(sbias + c)[i];
+                                v[4 * i] = fmaf(ln_rstd, v[4 * i], fmaf(ln_rm, u4.x, b4.x));
+                                v[4 * i + 1] = fmaf(ln_rstd, v[4 * i + 1], fmaf(ln_rm, u4.y, b4.y));
+                                v[4 * i + 2] = fmaf(ln_rstd, v[4 * i + 2], fmaf(ln_rm, u4.z, b4.z));
+                                v[4 * i + 3] = fmaf(ln_rstd, v[4 * i + 3], fmaf(ln_rm, u4.w, b4.w));
                             }
-                        }
-                        if (p.bias) {
+                        } else if (p.bias) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const float4 b4 = reinterpret_cast<const float4*>(sbias + c)[i];
@@ -575,19 +579,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                                 if (p.ln_u) {
                                     const float4 ua = reinterpret_cast<const float4*>(su + cc)[i];
                                     const float4 ug = reinterpret_cast<const float4*>(su + half_bn + cc)[i];
-                                    a0 = ln_rstd * (a0 - ln_mean * ua.x);
-                                    a1 = ln_rstd * (a1 - ln_mean * ua.y);
-                                    a2 = ln_rstd * (a2 - ln_mean * ua.z);
-                                    a3 = ln_rstd * (a3 - ln_mean * ua.w);
-                                    g0 = ln_rstd * (g0 - ln_mean * ug.x);
-                                    g1 = ln_rstd * (g1 - ln_mean * ug.y);
-                                    g2 = ln_rstd * (g2 - ln_mean * ug.z);
-                                    g3 = ln_rstd * (g3 - ln_mean * ug.w);
+                                    a0 = fmaf(ln_rstd, a0, fmaf(ln_rm, ua.x, ba.x));
+                                    a1 = fmaf(ln_rstd, a1, fmaf(ln_rm, ua.y, ba.y));
+                                    a2 = fmaf(ln_rstd, a2, fmaf(ln_rm, ua.z, ba.z));
+                                    a3 = fmaf(ln_rstd, a3, fmaf(ln_rm, ua.w, ba.w));
+                                    g0 = fmaf(ln_rstd, g0, fmaf(ln_rm, ug.x, bg.x));
+                                    g1 = fmaf(ln_rstd, g1, fmaf(ln_rm, ug.y, bg.y));
+                                    g2 = fmaf(ln_rstd, g2, fmaf(ln_rm, ug.z, bg.z));
+                                    g3 = fmaf(ln_rstd, g3, fmaf(ln_rm, ug.w, bg.w));
+                                } else {
+                                    a0 += ba.x, a1 += ba.y, a2 += ba.z, a3 += ba.w;
+                                    g0 += bg.x, g1 += bg.y, g2 += bg.z, g3 += bg.w;
                                 }
-                                const __half2 h0 = __floats2half2_rn((a0 + ba.x) * tc::gelu_erf_f(g0 + bg.x),
-                                                                     (a1 + ba.y) * tc::gelu_erf_f(g1 + bg.y));
-                                const __half2 h1 = __floats2half2_rn((a2 + ba.z) * tc::gelu_erf_f(g2 + bg.z),
-                                                                     (a3 + ba.w) * tc::gelu_erf_f(g3 + bg.w));
+                                const __half2 h0 = __floats2half2_rn(tc::geglu_mul(a0, g0), tc::geglu_mul(a1, g1));
+                                const __half2 h1 = __floats2half2_rn(tc::geglu_mul(a2, g2), tc::geglu_mul(a3, g3));
                                 pk[h16 * 8 + 2 * i] = *reinterpret_cast<const uint32_t*>(&h0);
                                 pk[h16 * 8 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&h1);
                             }
@@ -835,10 +840,16 @@ TileChoice choose_tiles(int tiles_m, int n_cols, int kblocks, int forced_bn, int
 }  // namespace
 
 extern "C" int tc_debug_read_gemm_trace(unsigned long long* host_dst, int count) {
+#if defined(TC_GEMM_TRACE) && TC_GEMM_TRACE
     if (!host_dst || count <= 0 || count > kTraceCtas * kTraceTiles * kTraceSlots)
         return tc_host::fail(TC_ERR_INVALID, "tc_debug_read_gemm_trace: bad count");
     return tc_host::check_cuda(cudaMemcpyFromSymbol(host_dst, g_tc_gemm_trace, (size_t)count * sizeof(unsigned long long)),
                                "tc_debug_read_gemm_trace");
+#else
+    (void)host_dst;
+    (void)count;
+    return tc_host::fail(TC_ERR_INVALID, "tc_debug_read_gemm_trace: library built without TC_BUILD_TRACE=1");
+#endif
 }
 
 extern "C" int tc_debug_set_gemm_mode(int mode) {
