@@ -155,6 +155,15 @@ def run_clip(model, sampler, di, S, fs):
     return video
 
 
+def workload_config(S):
+    """The `config` object of the JSON line (both arms name the same workload)."""
+    return {"workload": "ToonCrafter_512 320x512x16f DDIM-%d fp16, CFG 7.5 (cond+uncond batched), eta 1.0, "
+                        "uniform_trailing, guidance_rescale 0.7, sample() + decode T=16 + decode T=14; "
+                        "1 clip per GPU per step; random-init weights, synthetic inputs" % S,
+            "l2": "working set per clip (2.9 GB fp16 weights + activations) exceeds the 126 MB L2",
+            "baseline_note": "vs_baseline = value / 0.667 frames/s (README.md:222: ~24 s/clip on A100)"}
+
+
 # ---------------------------------------------------------------------------------------------------- roofline
 def gemm_roofline(model, dev):
     """Live per-launch CUDA-event timing of every tc_gemm_kernel launch of one eager UNet forward (B = 2)."""
@@ -240,7 +249,8 @@ def reference_arm(args):
     out = {"impl": "reference", "metric": "frames/sec (320x512x16f, DDIM-%d)" % S, "value": fps, "unit": "frames/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_fwd,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "ToonCrafter_512 320x512x16f DDIM-%d CFG 7.5, CPU" % S},
+           "config": dict(workload_config(S), reference_arm="same workload, reference algorithm (fp32 oracle port) on the host "
+                                                             "cores; each step is a bounded sample (one UNet forward)"),
            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -361,11 +371,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": fps_dev / (16.0 / 24.0) if S == 50 else None, "dtype": "f16",
         "data": "synthetic",
-        "config": {"workload": "ToonCrafter_512 320x512x16f DDIM-%d fp16, CFG 7.5 (cond+uncond batched), eta 1.0, "
-                               "uniform_trailing, guidance_rescale 0.7, sample() + decode T=16 + decode T=14; "
-                               "1 clip per GPU per step; random-init weights, synthetic inputs" % S,
-                   "l2": "working set per clip (2.9 GB fp16 weights + activations) exceeds the 126 MB L2",
-                   "baseline_note": "vs_baseline = value / 0.667 frames/s (README.md:222: ~24 s/clip on A100)"},
+        "config": workload_config(S),
         "sec_per_clip": ms_dev / args.steps / 1e3,
         "tflops_per_gpu": clip_tflop(S) / (ms_dev / args.steps / 1e3),
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes(hi),
