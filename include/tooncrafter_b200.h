@@ -172,6 +172,9 @@ int tc_phase_split2(const void* x, void* y, int N, int H, int W, int C, void* st
 int tc_copy2d(const void* src, long long lds, void* dst, long long ldd, long long rows, int cols, void* stream);
 /* y[r][c] += x[r][c] (Combiner add into first / last frame, autoencoder_dualref.py:357-368) */
 int tc_add2d(const void* x, long long ldx, void* y, long long ldy, long long rows, int cols, void* stream);
+/* y[r][c] = GELU(x[r][c]), exact erf form (nn.GELU of the Resampler feed-forward, lvdm/modules/encoders/resampler.py:27-34);
+ * y may alias x */
+int tc_gelu2d(const void* x, long long ldx, void* y, long long ldy, long long rows, int cols, void* stream);
 
 /* sinusoidal embedding (utils_diffusion.py:8-28) + Linear -> SiLU -> Linear MLP (openaimodel3d.py:370-382,550-577):
  * out[b][:] (+)= W2 * silu(W1 * sincos(t[b]) + b1) + b2, fp32 output.  dim = model_channels. */

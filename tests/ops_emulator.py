@@ -175,6 +175,10 @@ def add2d(x, y, *, rows, cols, ldx, ldy, x_offset=0, y_offset=0):
     v.copy_((v.float() + _view2d(x, rows, cols, ldx, x_offset).float()).half())
 
 
+def gelu2d(x, y, *, rows, cols, ldx, ldy, x_offset=0, y_offset=0):
+    _view2d(y, rows, cols, ldy, y_offset).copy_(F.gelu(_view2d(x, rows, cols, ldx, x_offset).float()).half())
+
+
 def time_embed(t, w1, b1, w2, b2, out, ws, *, dim, hidden, accumulate):
     half = dim // 2
     freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
@@ -209,7 +213,7 @@ def ddim_step(e_c, e_uc, x, noise, x_prev, pred_x0, coef, ws, *, B, n):
 
 _TABLE = {f.__name__: f for f in (conv_gemm, groupnorm, row_stats, layernorm, attention, temporal_attention, softmax_rows,
                                   ncthw_to_cl, cl_to_ncthw, upsample2x, phase_split2, copy2d, add2d, time_embed,
-                                  small_linear, ddim_step)}
+                                  small_linear, ddim_step, gelu2d)}
 
 
 def executor(fn, args, kw):

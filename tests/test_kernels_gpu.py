@@ -255,6 +255,17 @@ def test_groupnorm(ops, frames, fps, hw, C, silu, eps):
     _close(y, ref, "groupnorm")
 
 
+def test_gelu2d(ops):
+    """Exact-erf GELU on a strided matrix, in place (Resampler feed-forward, resampler.py:27-34)."""
+    rows, cols, ld = 300, 1024, 1280
+    buf = (_rand(rows, ld, seed=91) * 3).half()
+    ref = F.gelu(buf[:, :cols].float())
+    keep = buf[:, cols:].clone()
+    ops.gelu2d(buf, buf, rows=rows, cols=cols, ldx=ld, ldy=ld)
+    _close(buf[:, :cols], ref, "gelu2d")
+    assert torch.equal(buf[:, cols:], keep), "wrote outside the column range"
+
+
 @pytest.mark.parametrize("rows,C", [(1000, 320), (333, 640), (77, 1280), (64, 512)])
 def test_layernorm(ops, rows, C):
     x = (_rand(rows, C, seed=51) * 2 + 0.5).half()

@@ -95,6 +95,26 @@ __global__ void copy2d_kernel(const __half* __restrict__ src, long long lds, __h
     }
 }
 
+// y = GELU(x) (exact erf form, nn.GELU default) on a strided 2-D half matrix, in place allowed
+__global__ void gelu2d_kernel(const __half* __restrict__ x, long long ldx, __half* y, long long ldy, long long rows, int cols) {
+    tc::pdl_wait();
+    const int V = cols >> 3;
+    const long long total = rows * V;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / V;
+        const int v = (int)(i - r * V);
+        uint4 a = ld16(x + r * ldx + v * 8);
+        __half2* ha = reinterpret_cast<__half2*>(&a);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(ha[k]);
+            ha[k] = __floats2half2_rn(tc::gelu_erf_f(f.x), tc::gelu_erf_f(f.y));
+        }
+        st16(y + r * ldy + v * 8, a);
+    }
+}
+
 __global__ void add2d_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
                              long long rows, int cols) {
     tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
@@ -368,6 +388,18 @@ extern "C" int tc_add2d(const void* x, long long ldx, void* y, long long ldy, lo
         reinterpret_cast<const __half*>(x), ldx, reinterpret_cast<__half*>(y), ldy, rows, cols);
     count_launch();
     TC_CHECK_LAUNCH("add2d_kernel");
+    return TC_OK;
+}
+
+extern "C" int tc_gelu2d(const void* x, long long ldx, void* y, long long ldy, long long rows, int cols,
+                         void* stream_v) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    TC_CHECK_ARG(x && y && rows > 0 && cols > 0 && cols % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0,
+                 "tc_gelu2d: bad arguments");
+    tc_host::launch(gelu2d_kernel, dim3(grid_for(rows * (cols / 8), 256, 16 * sm_count())), dim3(256), 0, stream, 1,
+                    reinterpret_cast<const __half*>(x), ldx, reinterpret_cast<__half*>(y), ldy, rows, cols);
+    count_launch();
+    TC_CHECK_LAUNCH("gelu2d_kernel");
     return TC_OK;
 }
 

@@ -255,3 +255,39 @@ class Encoder(nn.Module):
         self.mid = Node(block_1=_vae_resnet(c, c), attn_1=_attn_block(c), block_2=_vae_resnet(c, c))
         self.norm_out = _gn(c, 1e-6)
         self.conv_out = nn.Conv2d(c, 2 * lay.z_channels if lay.double_z else lay.z_channels, 3, padding=1)
+
+
+# ------------------------------------------------------------------------------------ conditioning: image Resampler
+class Resampler(nn.Module):
+    """Drop-in for lvdm.modules.encoders.resampler.Resampler (same ctor kwargs, same state-dict keys): the perceiver
+    resampler that turns CLIP image tokens into the 16 x T image-context tokens of the UNet's cross-attention
+    (reference resampler.py:96-145, PerceiverAttention :49-93, FeedForward :27-34)."""
+
+    def __init__(self, dim=1024, depth=8, dim_head=64, heads=16, num_queries=8, embedding_dim=768, output_dim=1024,
+                 ff_mult=4, video_length=None):
+        super().__init__()
+        if dim_head != 64:
+            raise NotImplementedError("the attention kernel is specialised for 64-wide heads")
+        self.num_queries, self.video_length = num_queries, video_length
+        self.dim, self.depth, self.heads, self.dim_head = dim, depth, heads, dim_head
+        nq = num_queries * video_length if video_length is not None else num_queries
+        self.latents = nn.Parameter(torch.randn(1, nq, dim) / dim ** 0.5)
+        self.proj_in = nn.Linear(embedding_dim, dim)
+        self.proj_out = nn.Linear(dim, output_dim)
+        self.norm_out = nn.LayerNorm(output_dim)
+        inner = dim_head * heads
+        self.layers = nn.ModuleList()
+        for _ in range(depth):
+            attn = Node(norm1=nn.LayerNorm(dim), norm2=nn.LayerNorm(dim), to_q=nn.Linear(dim, inner, bias=False),
+                        to_kv=nn.Linear(dim, 2 * inner, bias=False), to_out=nn.Linear(inner, dim, bias=False))
+            ff = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, int(dim * ff_mult), bias=False), nn.GELU(),
+                               nn.Linear(int(dim * ff_mult), dim, bias=False))
+            self.layers.append(nn.ModuleList([attn, ff]))
+        self._engine = None
+
+    def forward(self, x):
+        """x [B, n_tokens, embedding_dim] (CLIP image tokens) -> [B, num_queries (* video_length), output_dim] fp32."""
+        from .cond_engine import ResamplerEngine
+        if self._engine is None or not self._engine.matches(self):
+            self._engine = ResamplerEngine(self)
+        return self._engine.forward(x).clone()

@@ -231,6 +231,13 @@ def add2d(x, y, *, rows, cols, ldx, ldy, x_offset=0, y_offset=0) -> None:
                        _stream()), "tc_add2d")
 
 
+def gelu2d(x, y, *, rows, cols, ldx, ldy, x_offset=0, y_offset=0) -> None:
+    """y = GELU(x), exact erf form; y may alias x."""
+    lib = _lib.load()
+    check(lib.tc_gelu2d(x.data_ptr() + 2 * x_offset, ldx, y.data_ptr() + 2 * y_offset, ldy, rows, cols, _stream()),
+          "tc_gelu2d")
+
+
 def time_embed(t: torch.Tensor, w1, b1, w2, b2, out: torch.Tensor, ws: torch.Tensor, *, dim: int, hidden: int,
                accumulate: bool) -> None:
     lib = _lib.load()
