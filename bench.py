@@ -148,10 +148,26 @@ def run_clip(model, sampler, di, S, fs):
                                 unconditional_conditioning=di["uncond"], eta=1.0, unconditional_guidance_scale=7.5,
                                 x_T=di["x_T"], fs=fs, timestep_spacing="uniform_trailing", guidance_rescale=0.7,
                                 verbose=False)
-    video = model.decode_first_stage(samples, ref_context=di["ref"])
     trimmed = torch.cat([samples[:, :, :1], samples[:, :, 2:-2], samples[:, :, -1:]], dim=2)   # drop frames 1 and 14
-    video2 = model.decode_first_stage(trimmed, ref_context=di["ref"])
-    video[:, :, 7:9] = video2[:, :, 6:8]                                                        # inference.py:264-270
+    group = getattr(sampler, "latency_group", None)
+    if group is None:
+        video = model.decode_first_stage(samples, ref_context=di["ref"])
+        video2 = model.decode_first_stage(trimmed, ref_context=di["ref"])
+        video[:, :, 7:9] = video2[:, :, 6:8]                                                    # inference.py:264-270
+        return video
+    # latency mode: both ranks hold identical samples; pair-rank 0 decodes the 16 frames, pair-rank 1 the 14-frame
+    # variant at the same time and ships its two middle frames over
+    import torch.distributed as dist
+    r = dist.get_rank(group)
+    if r == 0:
+        video = model.decode_first_stage(samples, ref_context=di["ref"])
+        patch = torch.empty_like(video[:, :, 7:9]).contiguous()
+    else:
+        video = model.decode_first_stage(trimmed, ref_context=di["ref"])
+        patch = video[:, :, 6:8].contiguous()
+    dist.broadcast(patch, src=dist.get_global_rank(group, 1), group=group)
+    if r == 0:
+        video[:, :, 7:9] = patch
     return video
 
 
@@ -266,6 +282,9 @@ def main():
     ap.add_argument("--ddim-steps", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--latency-mode", action="store_true",
+                    help="pairs of GPUs share one clip: each evaluates one classifier-free-guidance branch per step "
+                         "(one NCCL all-gather per step) and one of the two decodes; needs an even --gpus >= 2")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -286,7 +305,15 @@ def main():
     sampler = DDIMSampler(model)
     fs = torch.tensor([10], device=dev)
     from tooncrafter_b200.distributed import clip_seed, shard_clips
-    my_clip = shard_clips(world, rank, world)[0]           # one clip per GPU per step (weak scaling)
+    pair_group, in_pair = None, 0
+    if args.latency_mode:
+        if world < 2:
+            raise SystemExit("--latency-mode needs torchrun with an even number of GPUs >= 2")
+        from tooncrafter_b200.distributed import latency_pairs
+        pair_group, my_clip, in_pair = latency_pairs()     # one clip per GPU PAIR per step
+        sampler.latency_group = pair_group
+    else:
+        my_clip = shard_clips(world, rank, world)[0]       # one clip per GPU per step (weak scaling)
     hi = host_inputs(seed=clip_seed(123, my_clip))          # per-clip seed: results independent of the world size
     di = to_device(hi, dev)
     torch.cuda.synchronize()
@@ -332,7 +359,8 @@ def main():
     for _ in range(args.steps):
         dj = to_device(hi, dev)                            # H2D of this step's inputs from pinned memory
         video = run_clip(model, sampler, dj, S, fs)
-        out_host.copy_(video, non_blocking=True)           # D2H of the step's result
+        out_host[:, :, :video.shape[2]].copy_(video, non_blocking=True)   # D2H of the step's result (latency mode:
+                                                                          # pair-rank 1 holds the 14-frame variant)
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
@@ -363,17 +391,20 @@ def main():
         torch.cuda.synchronize()
         kernels_dec += ops.launch_count() - c0
     launches_per_clip = S * (kernels_unet + 2) + kernels_dec
-    clips = args.steps * world
+    clips = args.steps * (world // 2 if args.latency_mode else world)
     fps_dev = 16.0 * clips / (ms_dev / 1e3)
     fps_e2e = 16.0 * clips / (ms_e2e / 1e3)
     out = {
         "metric": "frames/sec (320x512x16f, DDIM-%d)" % S, "value": fps_dev, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": fps_dev / (16.0 / 24.0) if S == 50 else None, "dtype": "f16",
+        "scaling": "strong" if args.latency_mode else "weak",
+        "vs_baseline": fps_dev / (16.0 / 24.0) if S == 50 else None, "dtype": "f16",
         "data": "synthetic",
         "config": workload_config(S),
         "sec_per_clip": ms_dev / args.steps / 1e3,
-        "tflops_per_gpu": clip_tflop(S) / (ms_dev / args.steps / 1e3),
+        "mode": "latency (one clip per GPU pair: CFG branches split, all-gather per step)" if args.latency_mode
+                else "throughput (one clip per GPU)",
+        "tflops_per_gpu": clip_tflop(S) / (ms_dev / args.steps / 1e3) / (2 if args.latency_mode else 1),
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes(hi),
                 "d2h_bytes_per_step": out_host.numel() * out_host.element_size(),
                 "sec_per_clip": ms_e2e / args.steps / 1e3},

@@ -67,3 +67,40 @@ def test_two_rank_broadcast_and_timing_reduction():
     assert res["sigs"][0] == res["sigs"][1]                     # every rank holds rank 0's weights and buffers
     assert res["mx"] == 11.0                                     # max over ranks, not the local value
     assert res["clips"] == [[0, 1, 2], [3, 4]]
+
+
+def _pair_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        group, pair, in_pair = D.latency_pairs()
+        # the per-step exchange of latency mode: all-gather of the two guidance branches inside the pair
+        mine = torch.full((1, 4, 2, 3, 3), float(10 * pair + in_pair))
+        both = torch.empty(2 * mine.shape[0], *mine.shape[1:])            # concatenated along dim 0: [cond | uncond]
+        dist.all_gather_into_tensor(both, mine, group=group)
+        x = torch.full((3,), float(rank))
+        dist.broadcast(x, src=dist.get_global_rank(group, 0), group=group)      # what sync_pair_state does for x_T
+        res = [None] * world
+        dist.all_gather_object(res, dict(pair=pair, in_pair=in_pair, e_c=float(both[0].mean()), e_uc=float(both[1].mean()),
+                                         x=float(x[0])))
+        if rank == 0:
+            out.put(res)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_latency_pairs_two_rank_exchange():
+    """Latency mode plumbing on gloo: pair groups, the branch all-gather, the start-state broadcast."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pair_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r["pair"] for r in res] == [0, 0] and [r["in_pair"] for r in res] == [0, 1]
+    assert all(r["e_c"] == 0.0 and r["e_uc"] == 1.0 for r in res)        # slot 0 = conditional rank, slot 1 = unconditional
+    assert all(r["x"] == 0.0 for r in res)                               # pair-rank 0's start latent wins

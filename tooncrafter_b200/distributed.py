@@ -1,8 +1,14 @@
-"""Multi-GPU plumbing for the clip-parallel path: the reference shards prompts across ranks with no
+"""Multi-GPU plumbing.  Throughput mode — the clip-parallel path: the reference shards prompts across ranks with no
 collective on the data path (scripts/evaluation/inference.py:314-320, scripts/evaluation/ddp_wrapper.py:8-46).
 
 One process per GPU; the only collectives are ONE broadcast of the weights at init and the max-over-ranks of the
 timed region.  Backend "nccl" on GPUs (NVLink 5 / NVSwitch), "gloo" in the CPU tests.
+
+Latency mode (optional): pairs of adjacent ranks share ONE clip.  Classifier-free guidance needs two UNet
+evaluations per step (ddim.py:217-232); pair-rank 0 runs the conditional branch, pair-rank 1 the unconditional one
+(B = 1 each instead of one B = 2 forward), and one NCCL all-gather of the two fp16 predictions (2 x 327 KB at 320x512x16)
+per DDIM step is the only exchange: both ranks then apply the identical fused DDIM update.  `latency_pairs()` builds the
+groups, `DDIMSampler.latency_group` switches the sampler over.
 """
 from __future__ import annotations
 
@@ -61,3 +67,27 @@ def max_over_ranks(value: float, device="cpu") -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def latency_pairs():
+    """Process groups of adjacent rank pairs (0,1), (2,3), ...; returns (group of this rank, pair index, rank in pair).
+    Every rank must call this (new_group is collective).  World size must be even."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if world % 2:
+        raise ValueError("latency mode pairs GPUs: the world size must be even")
+    mine = None
+    for p in range(world // 2):
+        g = dist.new_group(ranks=[2 * p, 2 * p + 1])
+        if rank // 2 == p:
+            mine = g
+    return mine, rank // 2, rank % 2
+
+
+def sync_pair_state(x: torch.Tensor, group) -> None:
+    """Make the start latent and the CUDA RNG stream of a latency pair identical (pair-rank 0 wins), so that both ranks
+    draw the same per-step noise (ddim.py:273) and apply the same update."""
+    src = dist.get_global_rank(group, 0)
+    dist.broadcast(x, src=src, group=group)
+    state = torch.cuda.get_rng_state(x.device).to(x.device)
+    dist.broadcast(state, src=src, group=group)
+    torch.cuda.set_rng_state(state.cpu(), x.device)

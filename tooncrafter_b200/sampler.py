@@ -49,6 +49,9 @@ def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale=0.0):
 class DDIMSampler(object):
     def __init__(self, model, schedule="linear", **kwargs):
         super().__init__()
+        # optional: a 2-rank torch.distributed group (distributed.latency_pairs()); the fused path then evaluates one
+        # guidance branch per rank and all-gathers the two predictions every step
+        self.latency_group = None
         self.model = model
         self.ddpm_num_timesteps = model.num_timesteps
         self.schedule = schedule
@@ -196,18 +199,30 @@ class DDIMSampler(object):
             unet._engine = UNetEngine(unet)
         eng = unet._engine
         b, c, T, H, W = img.shape
-        B2 = 2 * b
-        ctx = torch.cat([torch.cat(cond["c_crossattn"], 1), torch.cat(uc["c_crossattn"], 1)], 0)
-        plan = eng.plan_for(B2, T, H, W, ctx.shape[1])
+        group = getattr(self, "latency_group", None)
+        if group is not None:
+            # latency mode: this rank evaluates ONE guidance branch (pair-rank 0: conditional, 1: unconditional)
+            import torch.distributed as dist
+            from .distributed import sync_pair_state
+            branch = dist.get_rank(group)
+            mine = cond if branch == 0 else uc
+            ctx = torch.cat(mine["c_crossattn"], 1)
+            cc = torch.cat(mine["c_concat"], 1)
+            nb = b
+        else:
+            ctx = torch.cat([torch.cat(cond["c_crossattn"], 1), torch.cat(uc["c_crossattn"], 1)], 0)
+            cc = torch.cat([torch.cat(cond["c_concat"], 1), torch.cat(uc["c_concat"], 1)], 0)
+            nb = 2 * b
+        B2 = nb
+        plan = eng.plan_for(nb, T, H, W, ctx.shape[1])
         eng.set_context(plan, ctx)
-        cc = torch.cat([torch.cat(cond["c_concat"], 1), torch.cat(uc["c_concat"], 1)], 0)
         plan.x_in[:, c:].copy_(cc)
         if eng.lay.fs_condition:
             if fs is None:
                 plan.fs_in.fill_(float(eng.lay.default_fs))
             else:
                 f = torch.as_tensor(fs, device=dev).to(torch.float32).reshape(-1)
-                plan.fs_in.copy_(torch.cat([f.expand(b), f.expand(b)]))
+                plan.fs_in.copy_(torch.cat([f.expand(b)] * (nb // b)))
         coef_table = torch.tensor([self.step_coefficients(total_steps - i - 1, cfg_scale, phi, temperature)
                                    for i in range(total_steps)], dtype=torch.float32, device=dev)
         t_table = torch.tensor([float(s) for s in time_range], dtype=torch.float32, device=dev)
@@ -216,15 +231,24 @@ class DDIMSampler(object):
         pred_x0 = torch.empty_like(x)
         ws = torch.empty(4 * b * ops.DDIM_PARTIALS, dtype=torch.float64, device=dev)
         n = c * T * H * W
+        if group is not None:
+            sync_pair_state(x, group)                                      # same x_T and same noise stream on both ranks
+            e_all = torch.empty((2 * b,) + tuple(plan.y_out.shape[1:]), dtype=plan.y_out.dtype, device=dev)   # [cond | uncond]
         for i in range(total_steps):
             index = total_steps - i - 1
             plan.x_in[:b, :c].copy_(x)
-            plan.x_in[b:, :c].copy_(x)
+            if group is None:
+                plan.x_in[b:, :c].copy_(x)
             plan.t_in.copy_(t_table[i].expand(B2))
             plan.main.replay(eng.use_graph)
             noise = torch.randn(x.shape, device=dev)                       # same draw order as ddim.py:273
-            y = plan.y_out
-            ops.ddim_step(y[:b], y[b:], x, noise, x_next, pred_x0, coef_table[i], ws, B=b, n=n)
+            if group is None:
+                y = plan.y_out
+                e_c, e_uc = y[:b], y[b:]
+            else:
+                dist.all_gather_into_tensor(e_all, plan.y_out, group=group)   # the step's only exchange (2 x 327 KB)
+                e_c, e_uc = e_all[:b], e_all[b:]
+            ops.ddim_step(e_c, e_uc, x, noise, x_next, pred_x0, coef_table[i], ws, B=b, n=n)
             x, x_next = x_next, x
             if callback:
                 callback(i)
