@@ -5,13 +5,25 @@
 //
 //   warp 0      TMA producer   : per k-block one 4-D box of the channels-last activation (im2col by
 //                                coordinate offset; out-of-bounds rows/cols are zero-filled by TMA == padding)
-//                                and one 2-D box of the [Cout][taps*C] weight matrix, 128B-swizzled
-//   warp 1      MMA issuer     : tcgen05.mma cta_group::1 kind::f16, M=128 x N=block_n x K=16, fp32 accum in TMEM,
-//                                two accumulator buffers so the epilogue of tile i overlaps the mainloop of i+1
-//   warps 2..9  epilogue       : tcgen05.ld (one output row per thread, two column groups) -> +bias, +embedding,
-//                                *scale, +residual, optional GEGLU -> fp16 -> 16-byte global stores
+//                                and one 2-D box of the [Cout][taps*C] weight matrix, 128B-swizzled.  Short-K launches
+//                                keep the whole weight N-tile resident in smem and stream only A.  A residual / skip
+//                                operand arrives as extra A-only k-blocks.
+//   warp 1      MMA issuer     : tcgen05.mma kind::f16, M=128 (cta_group::1) or M=256 (cta_group::2: two CTAs of a
+//                                cluster, each stages its own 128 A rows and half of the B tile), N=block_n, K=16, fp32
+//                                accumulators in TMEM, two buffers so the epilogue of tile i overlaps the mainloop of
+//                                i+1.  Residual k-blocks multiply by a 64x64 identity kept in smem (N=64 MMAs onto
+//                                accumulator columns [64r, 64r+64)): the skip add costs no epilogue instruction.
+//   warps 2..9  epilogue       : one output row per thread, 32-column chunks interleaved over two column groups;
+//                                tcgen05.ld (next chunk in flight) -> folded LayerNorm / bias / timestep embedding /
+//                                scale / GEGLU -> fp16 -> 64B-swizzled smem box -> TMA store (one 32x32 box per warp
+//                                where the tile geometry allows, else one 128x32 box per column group).  Optional
+//                                per-row {sum, sumsq} of the outputs for the consumer's LayerNorm fold.  Odd widths
+//                                (n_cols % 32 != 0, e.g. the 4-channel output conv) take the direct-store variant.
+//   Three instantiations of the epilogue (plain / GEGLU / direct-store) x {single CTA, CTA pair}; tile shape and pairing
+//   come from choose_tiles() (waves x per-tile cost with the tensor rate and the ~52 B/clk/SM L2->SM ingest bound).
 //
-// Roofline: tensor-bound (fp16 dense); algorithmic flops = 2 * M * n_cols * taps * C.
+// Roofline: tensor-bound for long K, L2-ingest-bound for 160-wide tiles, epilogue-issue-bound at K = 320 (profiles/);
+// algorithmic flops = 2 * M * n_cols * taps * C.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
