@@ -48,3 +48,31 @@ def test_unet_program_interpreted_on_cpu_matches_reference_golden():
     # every block boundary matches its geometry
     for _, name, act in plan.marks:
         assert act.rows * act.C > 0 and act.ld >= act.C
+
+
+def test_vae_encoder_and_decoder_programs_interpreted_on_cpu_match_reference_golden():
+    """Host logic of the two VAE engines (weight packing, tap tables, phase split, reference-context packing, arena
+    reuse) without a GPU: their recorded programs run on the PyTorch interpreter against the reference's outputs."""
+    from oracle import vae_oracle
+    from tiny_config import TINY_DDCONFIG
+    from tooncrafter_b200 import diffusion, layout, vae_engine
+    ae = diffusion.AutoencoderKL_Dualref(ddconfig=TINY_DDCONFIG, embed_dim=4).eval()
+    synthetic.fill_module_(ae, seed=SEED, prefix="first_stage_model.")
+    gi = golden_inputs()
+    # ---- encoder (+ quant_conv): moments and the five hidden maps
+    enc = vae_engine.EncoderEngine(ae, device="cpu", plan_only=True)
+    moments, hidden = enc.encode(gi["frames"], executor=ops_emulator.executor)
+    gm = torch.from_numpy(GOLD["enc_moments"])
+    assert (moments.float() - gm).abs().max().item() < 3e-2 * gm.abs().max().item()
+    for i, h in enumerate(hidden):
+        sub = torch.from_numpy(GOLD[f"enc_hidden{i}_sub"])
+        assert (h.float().flatten()[::97] - sub).abs().max().item() < 3e-2 * sub.abs().max().item() + 1e-2, i
+    # ---- decoder, fed with the fp32 oracle's hidden states (as the GPU test does)
+    sd = {"first_stage_model." + k: v for k, v in ae.state_dict().items()}
+    _, hid32 = vae_oracle.encode_hidden(sd, layout.encoder_layout(TINY_DDCONFIG), gi["frames"])
+    ref_ctx = [h.reshape(1, 2, *h.shape[1:]).permute(0, 2, 1, 3, 4).contiguous() for h in hid32]
+    zz = (gi["z"].permute(0, 2, 1, 3, 4).reshape(TINY_T, 4, 16, 16) / 0.18215).contiguous()
+    dec = vae_engine.DecoderEngine(ae.decoder, device="cpu", plan_only=True)
+    y = dec.decode(zz, ref_ctx, executor=ops_emulator.executor)
+    gold = torch.from_numpy(GOLD["decode"])[0].permute(1, 0, 2, 3)
+    assert (y.float() - gold).abs().max().item() < 3e-2 * gold.abs().max().item() + 1e-2
