@@ -9,6 +9,7 @@ import torch
 
 HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE))
+sys.path.insert(0, str(HERE / "golden"))
 
 from tiny_config import TINY_T, model_config  # noqa: E402
 
@@ -93,3 +94,36 @@ def test_multicond_guidance_formula():
     # e_uc + cfg_img (e_img - e_uc) + s (e_c - e_img)   (ddim_multiplecond.py:229-234)
     assert calls == ["c", "uc", "img"]
     assert torch.allclose(captured["v"], torch.full_like(x, 0.25 + 2.0 * (0.5 - 0.25) + 7.5 * (1.0 - 0.5)))
+
+
+def test_fused_path_on_the_emulator_matches_reference_golden():
+    """The fused sampler path (cond+uncond batched through the UNet program, context set once, device coefficient table,
+    fused DDIM update) with the recorded programs interpreted on CPU, against the REFERENCE's own 4-step sample."""
+    import numpy as np
+    import ops_emulator
+    from make_golden import SEED, golden_inputs
+    from tooncrafter_b200 import synthetic
+    from tooncrafter_b200.engine import UNetEngine
+    m = diffusion.instantiate_from_config(model_config())
+    synthetic.fill_module_(m, seed=SEED)
+    m = m.eval()
+    unet = m.model.diffusion_model
+    unet._engine = UNetEngine(unet, device="cpu", plan_only=True)
+    gi = golden_inputs()
+    it = iter(gi["noises"])
+    import tooncrafter_b200.sampler as smod
+    real = torch.randn
+    smod.torch.randn = lambda *a, **k: next(it)
+    try:
+        s = DDIMSampler(m)
+        s._test_executor = ops_emulator.executor
+        out, inter = s.sample(S=gi["S"], batch_size=1, shape=list(gi["x_T"].shape[1:]), conditioning=gi["cond"],
+                              unconditional_conditioning=gi["uncond"], eta=1.0, unconditional_guidance_scale=7.5,
+                              x_T=gi["x_T"], fs=gi["fs"], timestep_spacing="uniform_trailing", guidance_rescale=0.7,
+                              verbose=False)
+    finally:
+        smod.torch.randn = real
+    gold = torch.from_numpy(np.load(HERE / "golden" / "tiny_reference_outputs.npz")["ddim_samples"])
+    err = (out - gold).abs().max().item()
+    assert err < 3e-2 * gold.abs().max().item(), err      # fp16 activations in the interpreted UNet, 4 steps
+    assert len(inter["x_inter"]) >= 2 and out.dtype == torch.float32

@@ -52,6 +52,8 @@ class DDIMSampler(object):
         # optional: a 2-rank torch.distributed group (distributed.latency_pairs()); the fused path then evaluates one
         # guidance branch per rank and all-gathers the two predictions every step
         self.latency_group = None
+        # tests only: interpret the engine's recorded programs and the fused update on the PyTorch emulator (no GPU)
+        self._test_executor = None
         self.model = model
         self.ddpm_num_timesteps = model.num_timesteps
         self.schedule = schedule
@@ -121,7 +123,7 @@ class DDIMSampler(object):
                 and isinstance(uc, dict) and mask is None and not quantize and corrector is None
                 and noise_dropout == 0.0 and precision is None and not orig_steps and len(shape) == 5
                 and getattr(m.model, "conditioning_key", None) == "hybrid" and hasattr(unet, "layout")
-                and m.device.type == "cuda")
+                and (m.device.type == "cuda" or getattr(self, "_test_executor", None) is not None))
 
     @torch.no_grad()
     def ddim_sampling(self, cond, shape, x_T=None, ddim_use_original_steps=False, callback=None, timesteps=None,
@@ -215,7 +217,8 @@ class DDIMSampler(object):
             nb = 2 * b
         B2 = nb
         plan = eng.plan_for(nb, T, H, W, ctx.shape[1])
-        eng.set_context(plan, ctx)
+        ex = getattr(self, "_test_executor", None)
+        eng.set_context(plan, ctx, ex)
         plan.x_in[:, c:].copy_(cc)
         if eng.lay.fs_condition:
             if fs is None:
@@ -240,7 +243,10 @@ class DDIMSampler(object):
             if group is None:
                 plan.x_in[b:, :c].copy_(x)
             plan.t_in.copy_(t_table[i].expand(B2))
-            plan.main.replay(eng.use_graph)
+            if ex is None:
+                plan.main.replay(eng.use_graph)
+            else:
+                plan.main.run(ex)
             noise = torch.randn(x.shape, device=dev)                       # same draw order as ddim.py:273
             if group is None:
                 y = plan.y_out
@@ -248,7 +254,10 @@ class DDIMSampler(object):
             else:
                 dist.all_gather_into_tensor(e_all, plan.y_out, group=group)   # the step's only exchange (2 x 327 KB)
                 e_c, e_uc = e_all[:b], e_all[b:]
-            ops.ddim_step(e_c, e_uc, x, noise, x_next, pred_x0, coef_table[i], ws, B=b, n=n)
+            if ex is None:
+                ops.ddim_step(e_c, e_uc, x, noise, x_next, pred_x0, coef_table[i], ws, B=b, n=n)
+            else:
+                ex(ops.ddim_step, (e_c, e_uc, x, noise, x_next, pred_x0, coef_table[i], ws), dict(B=b, n=n))
             x, x_next = x_next, x
             if callback:
                 callback(i)
