@@ -76,3 +76,58 @@ def test_vae_encoder_and_decoder_programs_interpreted_on_cpu_match_reference_gol
     y = dec.decode(zz, ref_ctx, executor=ops_emulator.executor)
     gold = torch.from_numpy(GOLD["decode"])[0].permute(1, 0, 2, 3)
     assert (y.float() - gold).abs().max().item() < 3e-2 * gold.abs().max().item() + 1e-2
+
+
+def _check_conv_gemm_call(a, kw):
+    """Preconditions tc_conv_gemm documents / enforces (include/tooncrafter_b200.h, csrc/tc_gemm.cu TC_CHECK_ARG)."""
+    a_dims, a_strides, w, taps, out_dims, n_cols = a[1], a[2], a[3], a[4], a[6], a[7]
+    assert a_dims[3] > 0 and a_dims[3] % 64 == 0, "C must be a positive multiple of 64"
+    assert all(s % 8 == 0 for s in a_strides), "A strides must be multiples of 8 elements"
+    assert 1 <= len(taps) <= 9
+    assert w.shape[1] == len(taps) * a_dims[3] and w.shape[0] >= n_cols and w.stride(0) % 8 == 0
+    geglu = kw.get("geglu", False)
+    width = n_cols // 2 if geglu else n_cols
+    ldc = kw.get("ldc") or width
+    assert ldc % 8 == 0 and ldc >= width and all(d > 0 for d in out_dims) and n_cols > 0
+    for off in ("a_offset", "out_offset", "res_offset"):
+        assert kw.get(off, 0) % 8 == 0, "16-byte aligned operand slices"
+    if geglu:
+        bn = kw.get("block_n", 0)
+        assert bn > 0 and bn % 64 == 0 and n_cols % bn == 0 and kw.get("res") is None and kw.get("bias2") is None
+    if kw.get("res") is not None:
+        assert (kw.get("ldr") or n_cols) % 8 == 0
+    if kw.get("ln_stats") is not None:
+        assert kw.get("ln_u") is not None and n_cols % 16 == 0
+        if kw.get("ln_nslots", 0):
+            assert len(taps) == 1 and 1 <= kw["ln_nslots"] <= 64
+    if kw.get("row_stats") is not None:
+        bn = kw.get("block_n", 0)
+        assert bn > 0 and bn % 32 == 0 and not geglu and kw["row_stats_slots"] == -(-n_cols // bn)
+        assert kw["row_stats"].numel() >= 2 * kw["row_stats_slots"] * out_dims[0] * out_dims[1] * out_dims[2]
+
+
+def test_programs_plan_for_other_geometries_with_valid_launch_arguments():
+    """Planning is pure host logic: build the full-size UNet / VAE programs on the meta device for the 512 and the 1024
+    model geometry (configs/training_1024_v1.0: latent 72x128) and a small odd one, and check every recorded tc_conv_gemm
+    call against the C ABI's preconditions (no GPU, no memory)."""
+    from tiny_config import FULL_DDCONFIG, FULL_UNET
+    from tooncrafter_b200 import ops, vae_engine
+    with torch.device("meta"):
+        unet = modules.UNetModel(**FULL_UNET)
+        dec = modules.VideoDecoder(**FULL_DDCONFIG)
+    eng = engine.UNetEngine(unet, device="meta", plan_only=True)
+    for (B, T, H, W) in ((2, 16, 40, 64), (2, 16, 72, 128), (1, 16, 40, 64), (2, 8, 24, 40)):
+        plan = eng.plan_for(B, T, H, W, 77 + 16 * T)
+        calls = list(plan.ctx.calls) + list(plan.main.calls)
+        gemms = [(a, kw) for fn, a, kw in calls if fn is ops.conv_gemm]
+        assert len(plan.main) == 664 and len(gemms) > 400
+        for a, kw in gemms:
+            _check_conv_gemm_call(a, kw)
+        assert plan.arena.high_water < (170 << 30)
+    deng = vae_engine.DecoderEngine(dec, device="meta", plan_only=True)
+    for (T, h, w) in ((16, 40, 64), (14, 40, 64), (16, 72, 128)):
+        plan = deng.plan_for(T, h, w)
+        for fn, a, kw in list(plan.ctx.calls) + list(plan.main.calls):
+            if fn is ops.conv_gemm:
+                _check_conv_gemm_call(a, kw)
+        assert plan.arena.high_water < (170 << 30)

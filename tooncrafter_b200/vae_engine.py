@@ -67,7 +67,8 @@ class DecoderEngine:
             p.tn1, p.tn2 = pack_norm(ts.in_layers[0], dev), pack_norm(ts.out_layers[0], dev)
             p.t1_w, p.t1_b = pack_conv(ts.in_layers[2].weight, dev), _f(ts.in_layers[2].bias, dev)
             p.t2_w, p.t2_b = pack_conv(ts.out_layers[3].weight, dev), _f(ts.out_layers[3].bias, dev)
-            p.alpha = float(torch.sigmoid(m.mix_factor.detach().float()).item())
+            mf = m.mix_factor.detach().float()
+            p.alpha = 0.5 if mf.is_meta else float(torch.sigmoid(mf).item())    # meta: planning-only engines (host tests)
             return p
 
         self.cpad_in = (lay.z_channels + 63) // 64 * 64
