@@ -187,3 +187,18 @@ def test_reference_yaml_config_builds_our_classes_with_checkpoint_keys():
     assert all(sd[k] == man[k] for k in man)
     rs = json.loads((HERE / "golden" / "state_dict_manifest_resampler.json").read_text())
     assert {k: sd["image_proj_model." + k] for k in rs} == rs
+
+
+def test_missing_cuda_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU fallback: without the built .so (and without a way to build it) loading raises, it does not degrade."""
+    from tooncrafter_b200 import _lib, build as _build
+    monkeypatch.setattr(_lib, "_LIB", None)
+    monkeypatch.setattr(_lib, "lib_path", lambda: tmp_path / "libtooncrafter_b200.so")
+    monkeypatch.setattr(_build, "build", lambda *a, **k: (_ for _ in ()).throw(RuntimeError("nvcc not found")))
+    with pytest.raises(_lib.TcError):
+        _lib.load()
+    # and the engines refuse to run anywhere but on a GPU
+    from tooncrafter_b200.engine import UNetEngine
+    from tiny_config import TINY_UNET
+    with pytest.raises(RuntimeError):
+        UNetEngine(modules.UNetModel(**TINY_UNET))
