@@ -202,3 +202,16 @@ def test_missing_cuda_library_fails_loudly(monkeypatch, tmp_path):
     from tiny_config import TINY_UNET
     with pytest.raises(RuntimeError):
         UNetEngine(modules.UNetModel(**TINY_UNET))
+
+
+def test_product_code_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under tooncrafter_b200/, lvdm/ or utils/ may import it."""
+    import re
+    root = HERE.parent
+    offenders = []
+    for d in ("tooncrafter_b200", "lvdm", "utils"):
+        for f in (root / d).rglob("*.py"):
+            src = f.read_text()
+            if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M) or "import_module(\"oracle" in src:
+                offenders.append(str(f.relative_to(root)))
+    assert not offenders, offenders
