@@ -131,3 +131,39 @@ def test_programs_plan_for_other_geometries_with_valid_launch_arguments():
             if fn is ops.conv_gemm:
                 _check_conv_gemm_call(a, kw)
         assert plan.arena.high_water < (170 << 30)
+
+
+def test_freshly_allocated_contexts_are_never_served_from_a_stale_cache():
+    """Regression (round-1 ADVICE, engine.py set_context): callers build the conditioning as a fresh torch.cat
+    temporary per call; once the previous one is freed the allocator recycles its address with version 0 and the
+    same shape, so nothing pointer-derived identifies the content.  Six successive forwards with different,
+    immediately-freed contexts must each equal a forward through a brand-new engine."""
+    m = modules.UNetModel(**TINY_UNET)
+    synthetic.fill_module_(m, seed=SEED, prefix="model.diffusion_model.")
+    m.eval()
+    eng = engine.UNetEngine(m, device="cpu", plan_only=True)
+    gi = golden_inputs()["unet"]
+    seen_ptrs = []
+    for k in range(6):
+        g = torch.Generator().manual_seed(100 + k)
+        ctx = torch.cat([torch.randn(2, 77, gi["ctx"].shape[2], generator=g),
+                         torch.randn(2, gi["ctx"].shape[1] - 77, gi["ctx"].shape[2], generator=g)], 1)
+        seen_ptrs.append(ctx.data_ptr())
+        y = eng.forward(gi["x"], gi["t"], ctx, gi["fs"], executor=ops_emulator.executor).clone()
+        fresh = engine.UNetEngine(m, device="cpu", plan_only=True)
+        y_ref = fresh.forward(gi["x"], gi["t"], ctx, gi["fs"], executor=ops_emulator.executor)
+        assert torch.equal(y, y_ref), f"forward {k} used a stale conditioning"
+        del ctx
+    # (informational) the scenario is real when the allocator did recycle an address
+    print("distinct context addresses over 6 calls:", len(set(seen_ptrs)))
+
+
+def test_engine_repacks_when_any_parameter_changes():
+    """matches() fingerprints every parameter: an in-place edit of a LATE block (not the first tensor) re-packs."""
+    m = modules.UNetModel(**TINY_UNET)
+    synthetic.fill_module_(m, seed=SEED, prefix="model.diffusion_model.")
+    eng = engine.UNetEngine(m.eval(), device="cpu", plan_only=True)
+    assert eng.matches(m)
+    with torch.no_grad():
+        list(m.parameters())[-1].add_(1.0)
+    assert not eng.matches(m)

@@ -215,3 +215,22 @@ def test_product_code_never_imports_the_oracle():
             if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M) or "import_module(\"oracle" in src:
                 offenders.append(str(f.relative_to(root)))
     assert not offenders, offenders
+
+
+def test_utils_alias_covers_the_reference_surface():
+    """utils/utils.py shadows the reference's module when this repo is ahead on PYTHONPATH, so it must export every
+    public function of the reference file (lvdm/modules/encoders/condition.py imports count_params from it)."""
+    import ast
+    import importlib
+    ref = Path("/root/reference/utils/utils.py")
+    names = ({n.name for n in ast.parse(ref.read_text()).body if isinstance(n, ast.FunctionDef)} if ref.exists() else
+             {"count_params", "check_istarget", "instantiate_from_config", "get_obj_from_str", "load_npz_from_dir",
+              "load_npz_from_paths", "resize_numpy_image", "setup_dist"})
+    sys.modules.pop("utils.utils", None)
+    sys.modules.pop("utils", None)
+    mod = importlib.import_module("utils.utils")
+    assert Path(mod.__file__).resolve().parent.parent == Path(__file__).resolve().parent.parent
+    missing = sorted(n for n in names if not hasattr(mod, n))
+    assert not missing, f"utils.utils alias lacks {missing}"
+    assert mod.count_params(torch.nn.Linear(3, 4)) == 16
+    assert mod.check_istarget("a.b.attn2.to_k", ["attn2"]) and not mod.check_istarget("a.b", ["zz"])

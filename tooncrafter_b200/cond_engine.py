@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .engine import _P, _f, _h, linear, pack_linear
+from .engine import _P, _f, _h, linear, pack_linear, weights_signature
 from .runtime import Act, Arena, Builder, Program
 
 
@@ -24,7 +24,7 @@ class ResamplerEngine:
         self.plan_only = plan_only
         if self.dev.type != "cuda" and not plan_only:
             raise RuntimeError("tooncrafter_b200 runs on CUDA only (no CPU fallback); move the model to a GPU")
-        self._sig = (p0.data_ptr(), p0._version)
+        self._sig = weights_signature(rs)
         self.use_graph = use_graph
         self.dim, self.heads, self.inner = rs.dim, rs.heads, rs.heads * rs.dim_head
         self.n_lat = rs.latents.shape[1]
@@ -37,8 +37,7 @@ class ResamplerEngine:
         self._plans: Dict = {}
 
     def matches(self, rs) -> bool:
-        p0 = rs.latents
-        return self._sig == (p0.data_ptr(), p0._version) and p0.device == self.dev
+        return rs.latents.device == self.dev and self._sig == weights_signature(rs)
 
     def _pack(self, rs):
         dev = self.dev

@@ -187,6 +187,13 @@ def feed_forward(bld: Builder, x: Act, p: _P, out: Act, stats: Optional[RowStats
     hid.free()
 
 
+def weights_signature(module: nn.Module):
+    """Fingerprint of EVERY parameter and buffer (storage address + in-place version counter).  The module keeps its
+    tensors alive, so an address cannot be recycled while the signature is current; a partial load_state_dict, a LoRA
+    merge or an edit of a late block all bump a version counter and force a re-pack."""
+    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
 # ------------------------------------------------------------------------------------------------ the UNet engine
 class UNetEngine:
     def __init__(self, unet: nn.Module, device=None, arena_bytes: int = 0, use_graph: bool = True,
@@ -198,15 +205,16 @@ class UNetEngine:
         self.plan_only = plan_only
         if self.dev.type != "cuda" and not plan_only:
             raise RuntimeError("tooncrafter_b200 runs on CUDA only (no CPU fallback); move the model to a GPU")
-        self._sig = (p0.data_ptr(), p0._version)
+        self._sig = weights_signature(unet)
         self.use_graph = use_graph
         self.arena_bytes = arena_bytes
         self._pack(unet)
         self._plans: Dict = {}
 
     def matches(self, unet) -> bool:
+        """True while no parameter of `unet` was replaced, moved or written in place since packing."""
         p0 = next(unet.parameters())
-        return self._sig == (p0.data_ptr(), p0._version) and p0.device == self.dev
+        return p0.device == self.dev and self._sig == weights_signature(unet)
 
     # ---------------------------------------------------------------------------------- packing
     def _pack(self, u: nn.Module):
@@ -589,25 +597,27 @@ class UNetEngine:
         yo = bld.act(N, H, W, 16)
         gemm(bld, g, self.p_out.w, ops.TAPS_3x3, yo, bias=self.p_out.b, n_cols=lay.out_channels)
         main.add(ops.cl_to_ncthw, yo.t, plan.y_out, B=B, C_=lay.out_channels, T=T, H=H, W=W, ldx=16)
-        plan.ctx_key = None
+        plan.n_ctx = n_ctx
         return plan
 
     # ---------------------------------------------------------------------------------- execution
     def plan_for(self, B, T, H, W, n_ctx):
-        key = (B, T, H, W)
+        key = (B, T, H, W, n_ctx)
         if key not in self._plans:
             self._plans[key] = self._build(B, T, H, W, n_ctx)
         return self._plans[key]
 
     def set_context(self, plan, context: torch.Tensor, executor=None) -> None:
-        key = (context.data_ptr(), context._version, tuple(context.shape))
-        if plan.ctx_key == key:
-            return
+        """Copy the conditioning in and re-run the context K/V program — unconditionally.  Nothing about a caller's
+        tensor (address, version counter, shape) identifies its CONTENT once an earlier tensor has been freed: the
+        caching allocator hands the next `torch.cat` temporary the same block.  The program is 32 small GEMMs
+        (< 0.2 ms) per call, against 50 denoising steps per `sample()`."""
         B, T = plan.B, plan.T
+        if tuple(context.shape[:2]) != (B, plan.n_ctx):
+            raise ValueError(f"context {tuple(context.shape)} does not fit the plan ({B}, {plan.n_ctx}, ...)")
         plan.ctx_txt.copy_(context[:, :77].reshape(B * 77, -1))
         plan.ctx_img.copy_(context[:, 77:].reshape(B * T * 16, -1))
         plan.ctx.run(executor)
-        plan.ctx_key = key
 
     def load_inputs(self, plan, x, timesteps, fs) -> None:
         B = plan.B
