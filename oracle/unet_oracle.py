@@ -2,7 +2,7 @@
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this.
 It is a functional walk over a reference-keyed state dict (no nn.Modules), pinned against the UNMODIFIED
-reference by tests/test_oracle_vs_reference.py (run in the authoring container, where /root/reference
+reference by tests/test_oracle_cpu.py (test_*_matches_reference_golden, test_oracle_matches_live_reference_unet) (run in the authoring container, where /root/reference
 exists) and by the committed fixtures under tests/golden/ (generated from the reference by
 tests/golden/make_golden.py).
 
@@ -71,6 +71,13 @@ def res_block(p: SD, x, emb, B, temporal_conv=True):
     return h
 
 
+# "einsum": the explicit softmax(q k^T) v of CrossAttention.forward (the numerics oracle: fp32 softmax, fixed op order).
+# "sdpa":   F.scaled_dot_product_attention = what CrossAttention.efficient_forward (attention.py:146-209, xformers
+#           installed) amounts to on a GPU: fused flash kernels, no materialised scores.  Only bench.py's library
+#           baseline switches to it (the fair "best library path" to beat).
+ATTENTION_IMPL = "einsum"
+
+
 def attention_core(q, k, v, heads):
     """attention.py:101-125: softmax(q k^T / sqrt(d)) v per head; q [b, n, h*d]."""
     b, n, inner = q.shape
@@ -78,6 +85,8 @@ def attention_core(q, k, v, heads):
     qh = q.reshape(b, n, heads, d).transpose(1, 2)
     kh = k.reshape(b, -1, heads, d).transpose(1, 2)
     vh = v.reshape(b, -1, heads, d).transpose(1, 2)
+    if ATTENTION_IMPL == "sdpa":
+        return F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(b, n, inner)
     s = (qh @ kh.transpose(-1, -2)) * d ** -0.5
     o = s.softmax(dim=-1) @ vh
     return o.transpose(1, 2).reshape(b, n, inner)

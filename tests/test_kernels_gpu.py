@@ -1,10 +1,16 @@
 """Per-kernel numerics on the B200: every CUDA kernel (called through the C ABI) against a plain PyTorch fp32
 reference of the same op on the same fp16-rounded inputs.
 
-Tolerance (stated per SURVEY §7 "Numerics"): outputs are fp16 with fp32 accumulation, so the bound is a few fp16
-ulps of the output scale:  max|err| <= 3e-3 * max|ref| + 1e-3.
+Tolerance.  Outputs are fp16 with fp32 accumulation.  Two bounds are asserted per kernel:
+  * max-norm (SURVEY §7 "Numerics"): max|err| <= 3e-3 * max|ref| + 1e-3;
+  * the north-star's literal elementwise tolerance against the fp32 result: |out - ref| <= 1e-4 + 1e-3 |ref|
+    (rtol 1e-3 / atol 1e-4).  One fp16 ulp is 9.8e-4 relative at worst, so an output that is the correctly rounded
+    fp32 result passes, and so does a one-ulp rounding flip; the fraction of elements outside the tolerance is
+    printed and bounded by NS_MAX_VIOL (default 0: none) — kernels whose arithmetic is not a single fp32-accumulated
+    contraction pass their own measured bound explicitly (ns_max=...), with the reason at the call site.
 """
 import math
+import os
 
 import pytest
 import torch
@@ -15,14 +21,27 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _close(out, ref, what, rel=3e-3, abs_=1e-3):
+NS_RTOL, NS_ATOL = 1e-3, 1e-4
+NS_MAX_VIOL = float(os.environ.get("TC_NS_MAX_VIOL", "0"))   # survey runs set 1 to collect the fractions
+NS_LOG = os.environ.get("TC_NS_LOG")          # optional: append "what<TAB>violating fraction<TAB>max err" lines
+
+
+def _close(out, ref, what, rel=3e-3, abs_=1e-3, ns_max=None):
     out = out.float()
     ref = ref.float()
     assert out.shape == ref.shape, f"{what}: shape {out.shape} vs {ref.shape}"
     assert torch.isfinite(out).all(), f"{what}: non-finite output"
-    err = (out - ref).abs().max().item()
+    diff = (out - ref).abs()
+    err = diff.max().item()
     bound = rel * ref.abs().max().item() + abs_
+    viol = (diff > NS_ATOL + NS_RTOL * ref.abs()).float().mean().item()
+    print(f"{what}: max err {err:.3e} (bound {bound:.3e}); outside rtol 1e-3/atol 1e-4: {100 * viol:.4f} %")
+    if NS_LOG:
+        with open(NS_LOG, "a") as f:
+            f.write(f"{what}\t{viol:.3e}\t{err:.3e}\n")
     assert err <= bound, f"{what}: max err {err:.4e} > bound {bound:.4e} (ref max {ref.abs().max().item():.3e})"
+    lim = NS_MAX_VIOL if ns_max is None else ns_max
+    assert viol <= lim, f"{what}: {100 * viol:.4f} % of the outputs outside rtol 1e-3 / atol 1e-4 (allowed {100 * lim:.4f} %)"
     return err
 
 
@@ -40,6 +59,8 @@ def _pack_conv_w(w):
 @pytest.fixture(scope="module")
 def ops():
     from tooncrafter_b200 import ops as _ops
+    torch.backends.cuda.matmul.allow_tf32 = False     # the torch references below must be true fp32
+    torch.backends.cudnn.allow_tf32 = False
     # first cuDNN/cuBLAS use on a fresh box pages in ~1 GB of libraries: do it outside the per-test timeouts
     F.conv2d(torch.zeros(1, 8, 8, 8, device=DEV), torch.zeros(8, 8, 3, 3, device=DEV), padding=1)
     F.conv3d(torch.zeros(1, 8, 4, 8, 8, device=DEV), torch.zeros(8, 8, 3, 1, 1, device=DEV), padding=(1, 0, 0))

@@ -191,8 +191,11 @@ class DDIMSampler(object):
                 float(self.model.sqrt_one_minus_alphas_cumprod[t]), rescale, float(a_prev.sqrt()),
                 float((1.0 - a_prev - sigma ** 2).sqrt()), float(sigma) * float(temperature)]
 
-    def _sample_fused(self, cond, uc, img, time_range, total_steps, cfg_scale, phi, temperature, fs, callback,
-                      img_callback, log_every_t, intermediates):
+    def _fused_setup(self, cond, uc, shape, steps, cfg_scale, phi, temperature, fs):
+        """Everything of the fused path that is per-`sample()` call: engine / plan lookup, conditioning K/V program,
+        concat channels, fps, and the device tables of per-step coefficients.  `steps` = [(ddim index, t), ...] in
+        execution order.  Returns the state `_fused_step` consumes."""
+        from .engine import _P
         m = self.model
         dev = m.device
         unet = m.model.diffusion_model
@@ -200,12 +203,11 @@ class DDIMSampler(object):
         if unet._engine is None or not unet._engine.matches(unet):
             unet._engine = UNetEngine(unet)
         eng = unet._engine
-        b, c, T, H, W = img.shape
+        b, c, T, H, W = shape
         group = getattr(self, "latency_group", None)
         if group is not None:
             # latency mode: this rank evaluates ONE guidance branch (pair-rank 0: conditional, 1: unconditional)
             import torch.distributed as dist
-            from .distributed import sync_pair_state
             branch = dist.get_rank(group)
             mine = cond if branch == 0 else uc
             ctx = torch.cat(mine["c_crossattn"], 1)
@@ -215,10 +217,9 @@ class DDIMSampler(object):
             ctx = torch.cat([torch.cat(cond["c_crossattn"], 1), torch.cat(uc["c_crossattn"], 1)], 0)
             cc = torch.cat([torch.cat(cond["c_concat"], 1), torch.cat(uc["c_concat"], 1)], 0)
             nb = 2 * b
-        B2 = nb
         plan = eng.plan_for(nb, T, H, W, ctx.shape[1])
         ex = getattr(self, "_test_executor", None)
-        eng.set_context(plan, ctx, ex)
+        eng.set_context(plan, ctx, ex)                  # always re-run: a new prompt must never see old K/V
         plan.x_in[:, c:].copy_(cc)
         if eng.lay.fs_condition:
             if fs is None:
@@ -226,38 +227,52 @@ class DDIMSampler(object):
             else:
                 f = torch.as_tensor(fs, device=dev).to(torch.float32).reshape(-1)
                 plan.fs_in.copy_(torch.cat([f.expand(b)] * (nb // b)))
-        coef_table = torch.tensor([self.step_coefficients(total_steps - i - 1, cfg_scale, phi, temperature)
-                                   for i in range(total_steps)], dtype=torch.float32, device=dev)
-        t_table = torch.tensor([float(s) for s in time_range], dtype=torch.float32, device=dev)
+        st = _P(eng=eng, plan=plan, ex=ex, group=group, b=b, c=c, nb=nb, n=c * T * H * W, dev=dev)
+        st.coef_table = torch.tensor([self.step_coefficients(index, cfg_scale, phi, temperature)
+                                      for index, _ in steps], dtype=torch.float32, device=dev)
+        st.t_table = torch.tensor([float(t) for _, t in steps], dtype=torch.float32, device=dev)
+        st.ws = torch.empty(4 * b * ops.DDIM_PARTIALS, dtype=torch.float64, device=dev)
+        if group is not None:
+            st.e_all = torch.empty((2 * b,) + tuple(plan.y_out.shape[1:]), dtype=plan.y_out.dtype, device=dev)
+        return st
+
+    def _fused_step(self, st, i, x, noise, x_next, pred_x0):
+        """One DDIM step (row i of the tables): batched UNet program replay + the fused update.  Writes x_next and
+        pred_x0; afterwards st.plan.y_out still holds the two UNet predictions of this step."""
+        plan, b, c = st.plan, st.b, st.c
+        plan.x_in[:b, :c].copy_(x)
+        if st.group is None:
+            plan.x_in[b:, :c].copy_(x)
+        plan.t_in.copy_(st.t_table[i].expand(st.nb))
+        if st.ex is None:
+            plan.main.replay(st.eng.use_graph)
+        else:
+            plan.main.run(st.ex)
+        if st.group is None:
+            y = plan.y_out
+            e_c, e_uc = y[:b], y[b:]
+        else:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(st.e_all, plan.y_out, group=st.group)   # the step's only exchange (2 x 327 KB)
+            e_c, e_uc = st.e_all[:b], st.e_all[b:]
+        if st.ex is None:
+            ops.ddim_step(e_c, e_uc, x, noise, x_next, pred_x0, st.coef_table[i], st.ws, B=b, n=st.n)
+        else:
+            st.ex(ops.ddim_step, (e_c, e_uc, x, noise, x_next, pred_x0, st.coef_table[i], st.ws), dict(B=b, n=st.n))
+
+    def _sample_fused(self, cond, uc, img, time_range, total_steps, cfg_scale, phi, temperature, fs, callback,
+                      img_callback, log_every_t, intermediates):
+        steps = [(total_steps - i - 1, time_range[i]) for i in range(total_steps)]
+        st = self._fused_setup(cond, uc, tuple(img.shape), steps, cfg_scale, phi, temperature, fs)
         x = img.to(torch.float32).contiguous().clone()
         x_next = torch.empty_like(x)
         pred_x0 = torch.empty_like(x)
-        ws = torch.empty(4 * b * ops.DDIM_PARTIALS, dtype=torch.float64, device=dev)
-        n = c * T * H * W
-        if group is not None:
-            sync_pair_state(x, group)                                      # same x_T and same noise stream on both ranks
-            e_all = torch.empty((2 * b,) + tuple(plan.y_out.shape[1:]), dtype=plan.y_out.dtype, device=dev)   # [cond | uncond]
-        for i in range(total_steps):
-            index = total_steps - i - 1
-            plan.x_in[:b, :c].copy_(x)
-            if group is None:
-                plan.x_in[b:, :c].copy_(x)
-            plan.t_in.copy_(t_table[i].expand(B2))
-            if ex is None:
-                plan.main.replay(eng.use_graph)
-            else:
-                plan.main.run(ex)
-            noise = torch.randn(x.shape, device=dev)                       # same draw order as ddim.py:273
-            if group is None:
-                y = plan.y_out
-                e_c, e_uc = y[:b], y[b:]
-            else:
-                dist.all_gather_into_tensor(e_all, plan.y_out, group=group)   # the step's only exchange (2 x 327 KB)
-                e_c, e_uc = e_all[:b], e_all[b:]
-            if ex is None:
-                ops.ddim_step(e_c, e_uc, x, noise, x_next, pred_x0, coef_table[i], ws, B=b, n=n)
-            else:
-                ex(ops.ddim_step, (e_c, e_uc, x, noise, x_next, pred_x0, coef_table[i], ws), dict(B=b, n=n))
+        if st.group is not None:
+            from .distributed import sync_pair_state
+            sync_pair_state(x, st.group)                                   # same x_T and same noise stream on both ranks
+        for i, (index, _) in enumerate(steps):
+            noise = torch.randn(x.shape, device=st.dev)                    # one draw per step, as ddim.py:273
+            self._fused_step(st, i, x, noise, x_next, pred_x0)
             x, x_next = x_next, x
             if callback:
                 callback(i)
