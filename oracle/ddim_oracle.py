@@ -91,9 +91,10 @@ def rescale_noise_cfg(noise_cfg, noise_pred_text, phi):
 
 def ddim_update(x, e_c, e_uc, noise, co, cfg_scale, phi):
     """ddim.py:226-277 for the v-parameterisation with dynamic rescale (ddpm3d.py:240-252)."""
-    v = e_uc + cfg_scale * (e_c - e_uc)
+    v = e_uc + cfg_scale * (e_c - e_uc)          # in the dtype of the UNet outputs (fp16 under autocast, ddim.py:226)
     if phi > 0.0:
         v = rescale_noise_cfg(v, e_c, phi)
+    v = v.float()                                 # the schedule buffers are fp32: buffer * v promotes (ddpm3d.py:240-252)
     eps = co["sqrt_ac"] * v + co["sqrt_1mac"] * x
     x0 = (co["sqrt_ac"] * x - co["sqrt_1mac"] * v) * co["rescale"]
     x_prev = co["sqrt_aprev"] * x0 + co["dir_coef"] * eps + co["sigma"] * noise

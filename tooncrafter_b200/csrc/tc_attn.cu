@@ -38,6 +38,13 @@ __device__ __forceinline__ uint32_t pack_h2(float x, float y) {
     __half2 h = __floats2half2_rn(x, y);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+// (x, y) = hi + lo with hi = fp16(x, y) and lo = fp16 of the rounding residual
+__device__ __forceinline__ void split_h2(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x, y);
+    const float2 f = __half22float2(h);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = pack_h2(x - f.x, y - f.y);
+}
 
 // Ping-pong over TWO query tiles per CTA with specialised warps:
 //   warps 0-3 / 4-7 : softmax warpgroups for query tile 0 / 1 (one query row per thread)
@@ -565,11 +572,13 @@ __global__ void __launch_bounds__(128) temporal_attn_mma_kernel(const __half* __
         l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
         l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
         const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-        uint32_t pa[4];
-        pa[0] = pack_h2(sacc[0][0] * inv0, sacc[0][1] * inv0);
-        pa[1] = pack_h2(sacc[0][2] * inv1, sacc[0][3] * inv1);
-        pa[2] = pack_h2(sacc[1][0] * inv0, sacc[1][1] * inv0);
-        pa[3] = pack_h2(sacc[1][2] * inv1, sacc[1][3] * inv1);
+        // P = hi + lo with both parts fp16: with only T <= 16 keys per query the fp16 rounding of P is not averaged
+        // away, and the kernel is HBM-bound, so the second (residual) MMA is free
+        uint32_t pa[4], pl[4];
+        split_h2(sacc[0][0] * inv0, sacc[0][1] * inv0, pa[0], pl[0]);
+        split_h2(sacc[0][2] * inv1, sacc[0][3] * inv1, pa[1], pl[1]);
+        split_h2(sacc[1][0] * inv0, sacc[1][1] * inv0, pa[2], pl[2]);
+        split_h2(sacc[1][2] * inv1, sacc[1][3] * inv1, pa[3], pl[3]);
         __syncwarp();
         // ---- O = P V, V fragments by ldmatrix.trans (two 8-wide d tiles per instruction)
         __half* o0p = out + ((b * T + g) * P + pix) * ldo + h * 64;
@@ -585,6 +594,8 @@ __global__ void __launch_bounds__(128) temporal_attn_mma_kernel(const __half* __
                          : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
                          : "r"(addr));
             float oa[4] = {0.f, 0.f, 0.f, 0.f}, ob[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_m16n8k16(oa, pl, b0, b1);
+            mma_m16n8k16(ob, pl, b2, b3);
             mma_m16n8k16(oa, pa, b0, b1);
             mma_m16n8k16(ob, pa, b2, b3);
             if (r0) {
