@@ -1,0 +1,122 @@
+"""A/B of the attention kernels on the B200: second-generation kernel (TC_ATTN_IMPL=v2) vs the third generation with
+0..4 of every 8 exponential pairs on the FMA pipe (TC_ATTN_POLY).  For each variant: parity against torch fp32
+(max error, fraction outside rtol 1e-3 / atol 1e-4) on small / ragged shapes incl. data with large score ranges (forces
+the lazy-rescale path), then CUDA-event timings at the UNet level-0 and VAE fusion shapes.
+
+    python scripts/attn_ab.py [--quick]
+"""
+import argparse
+import os
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from tooncrafter_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def ref_attn(q, k, v, heads, kv_div=1):
+    B, Lq, _ = q.shape
+    k = k.repeat_interleave(kv_div, 0)[:B]
+    v = v.repeat_interleave(kv_div, 0)[:B]
+    sp = lambda t: t.float().reshape(t.shape[0], t.shape[1], heads, 64).transpose(1, 2)
+    s = (sp(q) @ sp(k).transpose(-1, -2)) * 64 ** -0.5
+    return (s.softmax(-1) @ sp(v)).transpose(1, 2).reshape(B, Lq, heads * 64)
+
+
+def run(q, k, v, heads, kv_div=1):
+    B, Lq, C = q.shape
+    out = torch.zeros_like(q)
+    ops.attention(q, [dict(k=k, v=v, ldk=C, ldv=C, Lk=k.shape[1], kv_div=kv_div)], out, q_batches=B, Lq=Lq, heads=heads,
+                  scale=64 ** -0.5, ldq=C, ldo=C)
+    return out
+
+
+def variants():
+    yield "v2", dict(TC_ATTN_IMPL="v2")
+    for p in (0, 1, 2, 3, 4):
+        yield f"v3 poly={p}/8", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY=str(p))
+
+
+def set_env(e):
+    for k in ("TC_ATTN_IMPL", "TC_ATTN_POLY"):
+        os.environ.pop(k, None)
+    os.environ.update(e)
+
+
+def parity():
+    g = torch.Generator().manual_seed(0)
+    cases = []
+    for (B, Lq, Lk, heads, kv_div, spread) in [(2, 300, 300, 2, 1, 1.0), (3, 128, 128, 1, 1, 1.0), (2, 2560, 2560, 5, 1, 1.0),
+                                               (4, 40, 40, 3, 1, 1.0), (1, 640, 640, 10, 1, 1.0), (2, 160, 160, 20, 1, 1.0),
+                                               (2, 500, 1000, 2, 1, 6.0), (4, 1024, 2048, 8, 4, 1.0), (2, 257, 129, 1, 1, 12.0),
+                                               (1, 256, 4096, 2, 1, 25.0)]:
+        C = heads * 64
+        q = (torch.randn(B, Lq, C, generator=g) * spread).half().to(DEV)
+        kb = (B + kv_div - 1) // kv_div
+        k = torch.randn(kb, Lk, C, generator=g).half().to(DEV)
+        # rows whose maximum keeps growing along the key axis: exercises the O rescale
+        k = k * torch.linspace(0.5, 2.0, Lk, device=DEV).half()[None, :, None]
+        v = torch.randn(kb, Lk, C, generator=g).half().to(DEV)
+        cases.append((f"B{B} Lq{Lq} Lk{Lk} h{heads} div{kv_div} x{spread}", q, k, v, heads, kv_div))
+    ok = True
+    for name, env in variants():
+        set_env(env)
+        worst, worst_v = 0.0, 0.0
+        for cname, q, k, v, heads, kv_div in cases:
+            out = run(q, k, v, heads, kv_div).float()
+            torch.cuda.synchronize()
+            ref = ref_attn(q, k, v, heads, kv_div)
+            d = (out - ref).abs()
+            viol = (d > 1e-4 + 1e-3 * ref.abs()).float().mean().item()
+            bad = not torch.isfinite(out).all().item() or d.max().item() > 3e-3 * ref.abs().max().item() + 1e-3
+            if bad:
+                ok = False
+                print(f"  !! {name}: {cname}: max err {d.max().item():.3e} (ref max {ref.abs().max().item():.2f}) viol {viol:.2e}")
+            worst, worst_v = max(worst, d.max().item()), max(worst_v, viol)
+        print(f"parity {name:14s}: worst max err {worst:.3e}, worst fraction outside rtol 1e-3/atol 1e-4 {worst_v:.2e}", flush=True)
+    return ok
+
+
+def timing(quick):
+    shapes = [("unet L0 self  (32 x 5 heads, L 2560)", 32, 2560, 2560, 5, 1),
+              ("unet L1 self  (32 x 10 heads, L 640)", 32, 640, 640, 10, 1),
+              ("vae fusion    (16 x 8 heads, 10240 x 20480)", 16, 10240, 20480, 8, 16)]
+    if quick:
+        shapes = shapes[:2]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    for sname, B, Lq, Lk, heads, kv_div in shapes:
+        C = heads * 64
+        q = torch.randn(B, Lq, C, device=DEV).half()
+        kb = (B + kv_div - 1) // kv_div
+        k = torch.randn(kb, Lk, C, device=DEV).half()
+        v = torch.randn(kb, Lk, C, device=DEV).half()
+        fl = 4.0 * B * heads * Lq * Lk * 64
+        for name, env in variants():
+            set_env(env)
+            for _ in range(3):
+                run(q, k, v, heads, kv_div)
+            ts = []
+            for _ in range(7):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                run(q, k, v, heads, kv_div)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ts.sort()
+            ms = ts[len(ts) // 2]
+            print(f"time {sname:46s} {name:14s}: {ms * 1e3:9.1f} us  {fl / ms / 1e9:7.1f} TF/s", flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    a = ap.parse_args()
+    good = parity()
+    timing(a.quick)
+    print("PARITY_OK" if good else "PARITY_FAILED")

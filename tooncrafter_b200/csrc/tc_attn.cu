@@ -7,6 +7,7 @@
 //  tc_softmax_rows        row softmax for the unfused d=512 VAE mid-block attention.
 //
 // Reference sites: lvdm/modules/attention.py:81-209,365-412; lvdm/models/autoencoder_dualref.py:172-200,270-341.
+#include <stdlib.h>
 #include "tc_common.cuh"
 #include "tc_host.h"
 
@@ -645,12 +646,30 @@ __global__ void softmax_rows_kernel(__half* __restrict__ s, long long lds, int r
 
 using namespace tc_host;
 
+int tc_attention_v3(const TcAttention* d, int poly_of_8, cudaStream_t stream);   // tc_attn3.cu
+
+// TC_ATTN_IMPL=v2 keeps single-segment problems on the second-generation kernel below (A/B runs);
+// TC_ATTN_POLY=n (0..4) sets how many of every 8 exponential pairs the v3 kernel evaluates on the FMA pipe.
+static int attn_impl_v3() {
+    const char* e = getenv("TC_ATTN_IMPL");
+    return !(e && e[0] == 'v' && e[1] == '2');
+}
+static int attn_poly() {
+    const char* e = getenv("TC_ATTN_POLY");
+    return (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 0;
+}
+
 extern "C" int tc_attention(const TcAttention* d, void* stream_v) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     TC_CHECK_ARG(d && d->q && d->out, "tc_attention: null pointer");
     TC_CHECK_ARG(d->n_seg == 1 || d->n_seg == 2, "tc_attention: n_seg must be 1 or 2");
     TC_CHECK_ARG(d->q_batches > 0 && d->Lq > 0 && d->heads > 0, "tc_attention: empty problem");
     TC_CHECK_ARG(d->ldq % 8 == 0 && d->ldo % 8 == 0, "tc_attention: strides must be multiples of 8");
+    if (d->n_seg == 1 && attn_impl_v3()) {
+        TC_CHECK_ARG(d->k[0] && d->v[0] && d->Lk[0] > 0 && d->kv_div[0] > 0, "tc_attention: bad kv segment");
+        TC_CHECK_ARG(d->ldk[0] % 8 == 0 && d->ldv[0] % 8 == 0, "tc_attention: kv strides must be multiples of 8");
+        return tc_attention_v3(d, attn_poly(), stream);
+    }
     AttnKParams p;
     memset(&p, 0, sizeof(p));
     const uint32_t box[3] = {64, 128, 1};

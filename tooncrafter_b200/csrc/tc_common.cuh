@@ -186,6 +186,42 @@ __device__ __forceinline__ void bulk_wait_group() {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// registers -> TMEM: this warp's 32 lanes x N consecutive 32-bit columns (lane i <- thread i)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 rows = TMEM lanes, K-major, 16-bit elements packed two per
+// 32-bit column, K = 16 per instruction = 8 columns) is read from tensor memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // CTA-pair (cta_group::2) variants: two SMs of a cluster cooperate on one M = 256 tile
@@ -292,6 +328,58 @@ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t M, uint32_t N, uint3
     return d;
 }
 
+// ---------------------------------------------------------------------------------------------
+// packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2): one issue slot per TWO values.  The pipe rate per value is the
+// scalar one (measured: profiles/r02_pipe_rates.txt), the win is instruction issue, which bounds the GEMM epilogues
+// and the attention softmax.
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 pk2u(uint32_t lo, uint32_t hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void unpk2u(f32x2 v, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// fp16 pair from an fp32 pair (low element -> low half)
+__device__ __forceinline__ uint32_t h2_from_f2(f32x2 v) {
+    float lo, hi;
+    unpk2(v, lo, hi);
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// fp32 pair from an fp16 pair
+__device__ __forceinline__ f32x2 f2_from_h2(uint32_t h) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+    return pk2(f.x, f.y);
+}
+
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // erf by Abramowitz & Stegun 7.1.28: 1 - (1 + a1 x + ... + a6 x^6)^-16, |err| <= 3e-7: 6 FMA + 4 squarings + ONE
@@ -335,6 +423,34 @@ __device__ __forceinline__ float geglu_mul(float a, float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(t));
     const float phi = x >= 0.f ? 1.0f - h : h;
     return (a * x) * phi;
+}
+
+
+// Two GEGLU products at once: (a * x * Phi(x)) for the pairs a = (a0, a1), x = (g0, g1) — the same A&S 7.1.28 form as
+// geglu_mul with the polynomial, the four squarings and the final products on packed FFMA2 / FMUL2 (half the issue
+// slots), |x| by clearing sign bits (ALU pipe) and the reciprocal on MUFU.
+__device__ __forceinline__ f32x2 geglu_mul2(f32x2 a, f32x2 x) {
+    uint32_t x0, x1;
+    unpk2u(x, x0, x1);
+    const f32x2 ax = pk2u(x0 & 0x7fffffffu, x1 & 0x7fffffffu);
+    f32x2 t = fma2(ax, pk2(5.6212996640e-06f, 5.6212996640e-06f), pk2(5.1055209009e-05f, 5.1055209009e-05f));
+    t = fma2(t, ax, pk2(3.9686137011e-05f, 3.9686137011e-05f));
+    t = fma2(t, ax, pk2(3.4227392389e-03f, 3.4227392389e-03f));
+    t = fma2(t, ax, pk2(2.2076998457e-02f, 2.2076998457e-02f));
+    t = fma2(t, ax, pk2(5.2075163037e-02f, 5.2075163037e-02f));
+    t = fma2(t, ax, pk2(1.0442737824e+00f, 1.0442737824e+00f));
+    t = mul2(t, t);
+    t = mul2(t, t);
+    t = mul2(t, t);
+    t = mul2(t, t);
+    float t0, t1, h0, h1;
+    unpk2(t, t0, t1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(h0) : "f"(t0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(t1));
+    // Phi = 1 - h for x >= 0, h for x < 0
+    const float p0 = (x0 >> 31) ? h0 : 1.0f - h0;
+    const float p1 = (x1 >> 31) ? h1 : 1.0f - h1;
+    return mul2(mul2(a, x), pk2(p0, p1));
 }
 
 }  // namespace tc

@@ -60,6 +60,7 @@ struct alignas(64) GemmKParams {
     int tiles_x, tiles_y, tiles_n;  // spatial tiling of the M dimension
     int tiles_m, tiles_nn;          // tiles along M and along N
     int BN;
+    int raster;                     // tile order, see TC_DECODE_TILE
     int n_cols;
     int stages;
     uint32_t a_bytes;  // bytes delivered per A box
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     // output staging for the TMA-store epilogue: one 128-row x 32-column (64 B, 64B-swizzled) box per column group
     uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_epi + 1024) + 1023) & ~uintptr_t(1023));
     // 64 x 64 identity (K-major, 128B-swizzled like a weight tile): the B operand of the residual k-blocks
-    uint8_t* s_eye = s_stage + 16384;
+    uint8_t* s_eye = s_stage + 32768;                     // two staging boxes (16 KiB each) in rotation
     // producer-side row statistics: column group 1 hands its partials to group 0 (two buffers by tile parity)
     float2* s_rs = reinterpret_cast<float2*>(s_eye + 8192);
 
@@ -213,9 +214,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     const int kblocks = main_kblocks + p.res_kblocks;   // consumer view (residual k-blocks included)
     // tile -> (nt, mt) for this CTA; mt >= tiles_m (odd tail of a pair) decodes to out-of-range coordinates:
     // its TMA boxes are zero-filled and its rows are never stored
+    // raster 0: N-tile-major (all M tiles of weight tile 0, then tile 1, ...: the resident-weight order);
+    // raster 1: N tile fastest — the CTAs that run side by side work on the SAME rows of A with different weight tiles,
+    // so A comes from DRAM once and from L2 for the other N tiles (the N-major order streamed the 100-200 MB A operand
+    // of the FF2 GEMMs once per N tile: 2-3.3x DRAM traffic, profiles/r01_unet_b2_launches_final.txt).  The host makes
+    // the number of work units a multiple of tiles_nn when the weights are resident, so a CTA's N tile never changes.
+#define TC_TILE_NT(tile) (p.raster ? (tile) % p.tiles_nn : (tile) / tiles_mu)
 #define TC_DECODE_TILE(tile)                                                   \
-    const int nt = (tile) / tiles_mu;                                          \
-    const int mt = ((tile) - nt * tiles_mu) * (kPair ? 2 : 1) + (int)rank;     \
+    const int nt = TC_TILE_NT(tile);                                           \
+    const int mtu_ = p.raster ? (tile) / p.tiles_nn : (tile) - nt * tiles_mu;  \
+    const int mt = mtu_ * (kPair ? 2 : 1) + (int)rank;                         \
     const int tx = mt % p.tiles_x;                                             \
     const int ty = (mt / p.tiles_x) % p.tiles_y;                               \
     const int tn = mt / (p.tiles_x * p.tiles_y);
@@ -324,10 +332,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             uint32_t bphase = 0;
             int ti = 0;
             for (int tile = unit; tile < total_tiles; tile += n_units, ++ti) {
-                if (p.b_resident && tile / tiles_mu != cur_nt) {
+                if (p.b_resident && TC_TILE_NT(tile) != cur_nt) {
                     tc::mbar_wait(bfull_bar, bphase);
                     bphase ^= 1u;
-                    cur_nt = tile / tiles_mu;
+                    cur_nt = TC_TILE_NT(tile);
                 }
                 tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
                 tc::tc_fence_after();
@@ -365,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     if constexpr (kPair) tc::umma_commit_pair(&tfull_bar[acc]); else tc::umma_commit(&tfull_bar[acc]);
                     // last tile on this weight N-tile: tell the producer(s) when its MMAs have drained
                     const int next = tile + n_units;
-                    if (p.b_resident && next < total_tiles && next / tiles_mu != cur_nt) {
+                    if (p.b_resident && next < total_tiles && TC_TILE_NT(next) != cur_nt) {
                         if constexpr (kPair) tc::umma_commit_pair(bfree_bar); else tc::umma_commit(bfree_bar);
                     }
                 }
@@ -404,6 +412,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         const int wx = (q * 32) % p.TW, wy = ((q * 32) / p.TW) % p.TH, wn = (q * 32) / (p.TW * p.TH);
         const bool warp_rows_in_tile = q * 32 < p.TW * p.TH * p.TN;
         int staged_nt = -1, sb = 1;
+        uint32_t n_stores = 0;   // TMA-store chunks issued so far by this warp / column group: picks the staging box
         int acc = 0;
         uint32_t acc_phase = 0;
         int ti = 0;
@@ -474,16 +483,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             if (g_tc_gemm_debug & 2) {
                 // (profiling) accumulator is dropped: measures mainloop + handshake only
             } else if constexpr (kEpi != 2) {
-                // ---- TMEM -> registers -> swizzled smem box -> one TMA store per 128 x 32 chunk.  Per-thread 16-byte
+                // ---- TMEM -> registers -> swizzled smem box -> one TMA store per 32-column chunk.  Per-thread 16-byte
                 // global stores touch 32 different lines per instruction (LSU: 16 B/clk instead of 128 B/clk) and cost
-                // 30-35 % of the K = 320 launches (scripts/prof_epilogue.py, mode 0 vs 1).
+                // 30-35 % of the K = 320 launches (scripts/prof_epilogue.py, mode 0 vs 1).  The arithmetic runs on
+                // packed fp32 pairs (FFMA2 / FADD2 / FMUL2): the epilogue is instruction-issue bound at K = 320, and the
+                // staging box is double-buffered so a chunk never waits for the previous chunk's TMA store to drain
+                // (the in-kernel timeline showed ~1400 cycles per chunk, mostly that wait).
                 const int half_bn = BN >> 1;
                 const __half* b2row =
                     p.bias2 ? p.bias2 + (row_ok ? (m / p.bias2_rows_per) : 0) * p.bias2_ld + (long long)nt * BN : nullptr;
                 const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
                 const int dbg = g_tc_gemm_debug;
+                const tc::f32x2 rstd2 = tc::pk2(ln_rstd, ln_rstd), rm2 = tc::pk2(ln_rm, ln_rm);
+                const tc::f32x2 scale2 = tc::pk2(p.acc_scale, p.acc_scale);
                 uint32_t r[32];
-                float rs_sum = 0.f, rs_sq = 0.f;
+                tc::f32x2 rs_sum2 = 0ull, rs_sq2 = 0ull;
                 if (kEpi == 0 && cg * 32 < width) tc::tmem_ld32(taddr + (uint32_t)(cg * 32), r);
 #pragma unroll 1
                 for (int jc = 0; jc < 4; ++jc) {
@@ -498,74 +512,61 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                             for (int hh = 0; hh < 4; ++hh) rr[hh] = *reinterpret_cast<const uint4*>(rrow + c + hh * 8);
                         }
                         tc::tmem_ld_wait();
-                        float v[32];
+                        tc::f32x2 v[16];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                        for (int i = 0; i < 16; ++i) v[i] = tc::pk2u(r[2 * i], r[2 * i + 1]);
+                        // next chunk's accumulator read flies while this one is finished, staged and stored
+                        if (c + 64 < width) tc::tmem_ld32(taddr + (uint32_t)(c + 64), r);
                         if (p.ln_u) {
-                            // rstd*(acc - mean*u) + bias  ==  rstd*acc + (bias - rstd*mean*u): two FFMAs per value
+                            // rstd*(acc - mean*u) + bias  ==  rstd*acc + (bias - rstd*mean*u): two packed FMAs per pair
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const float4 u4 = reinterpret_cast<const float4*>(su + c)[i];
                                 float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                                 if (p.bias) b4 = reinterpret_cast<const float4*>(sbias + c)[i];
-                                v[4 * i] = fmaf(ln_rstd, v[4 * i], fmaf(ln_rm, u4.x, b4.x));
-                                v[4 * i + 1] = fmaf(ln_rstd, v[4 * i + 1], fmaf(ln_rm, u4.y, b4.y));
-                                v[4 * i + 2] = fmaf(ln_rstd, v[4 * i + 2], fmaf(ln_rm, u4.z, b4.z));
-                                v[4 * i + 3] = fmaf(ln_rstd, v[4 * i + 3], fmaf(ln_rm, u4.w, b4.w));
+                                v[2 * i] = tc::fma2(rstd2, v[2 * i], tc::fma2(rm2, tc::pk2(u4.x, u4.y), tc::pk2(b4.x, b4.y)));
+                                v[2 * i + 1] = tc::fma2(rstd2, v[2 * i + 1], tc::fma2(rm2, tc::pk2(u4.z, u4.w), tc::pk2(b4.z, b4.w)));
                             }
                         } else if (p.bias) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const float4 b4 = reinterpret_cast<const float4*>(sbias + c)[i];
-                                v[4 * i] += b4.x;
-                                v[4 * i + 1] += b4.y;
-                                v[4 * i + 2] += b4.z;
-                                v[4 * i + 3] += b4.w;
+                                v[2 * i] = tc::add2(v[2 * i], tc::pk2(b4.x, b4.y));
+                                v[2 * i + 1] = tc::add2(v[2 * i + 1], tc::pk2(b4.z, b4.w));
                             }
                         }
                         if (b2row) {
 #pragma unroll
                             for (int hh = 0; hh < 4; ++hh) {
                                 const uint4 u = __ldg(reinterpret_cast<const uint4*>(b2row + c) + hh);
-                                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const float2 f = __half22float2(h2[i]);
-                                    v[hh * 8 + 2 * i] += f.x;
-                                    v[hh * 8 + 2 * i + 1] += f.y;
-                                }
+                                v[4 * hh] = tc::add2(v[4 * hh], tc::f2_from_h2(u.x));
+                                v[4 * hh + 1] = tc::add2(v[4 * hh + 1], tc::f2_from_h2(u.y));
+                                v[4 * hh + 2] = tc::add2(v[4 * hh + 2], tc::f2_from_h2(u.z));
+                                v[4 * hh + 3] = tc::add2(v[4 * hh + 3], tc::f2_from_h2(u.w));
                             }
                         }
                         if (p.acc_scale != 1.0f) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] *= p.acc_scale;
+                            for (int i = 0; i < 16; ++i) v[i] = tc::mul2(v[i], scale2);
                         }
                         if (rrow) {
 #pragma unroll
                             for (int hh = 0; hh < 4; ++hh) {
-                                const __half2* h2 = reinterpret_cast<const __half2*>(&rr[hh]);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const float2 f = __half22float2(h2[i]);
-                                    v[hh * 8 + 2 * i] += f.x;
-                                    v[hh * 8 + 2 * i + 1] += f.y;
-                                }
+                                v[4 * hh] = tc::add2(v[4 * hh], tc::f2_from_h2(rr[hh].x));
+                                v[4 * hh + 1] = tc::add2(v[4 * hh + 1], tc::f2_from_h2(rr[hh].y));
+                                v[4 * hh + 2] = tc::add2(v[4 * hh + 2], tc::f2_from_h2(rr[hh].z));
+                                v[4 * hh + 3] = tc::add2(v[4 * hh + 3], tc::f2_from_h2(rr[hh].w));
                             }
                         }
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-                            pk[i] = *reinterpret_cast<const uint32_t*>(&h);
-                        }
-                        // next chunk's accumulator read flies while this one is staged and stored
-                        if (c + 64 < width) tc::tmem_ld32(taddr + (uint32_t)(c + 64), r);
+                        for (int i = 0; i < 16; ++i) pk[i] = tc::h2_from_f2(v[i]);
                         if (p.row_stats) {
                             // statistics of the values the consumer will read: the fp16-rounded outputs
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
-                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pk[i]));
-                                rs_sum += f.x + f.y;
-                                rs_sq = fmaf(f.x, f.x, fmaf(f.y, f.y, rs_sq));
+                                const tc::f32x2 f = tc::f2_from_h2(pk[i]);
+                                rs_sum2 = tc::add2(rs_sum2, f);
+                                rs_sq2 = tc::fma2(f, f, rs_sq2);
                             }
                         }
                     } else {
@@ -584,41 +585,38 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                                     ba = reinterpret_cast<const float4*>(sbias + cc)[i];
                                     bg = reinterpret_cast<const float4*>(sbias + half_bn + cc)[i];
                                 }
-                                float a0 = __uint_as_float(ra[4 * i]), a1 = __uint_as_float(ra[4 * i + 1]);
-                                float a2 = __uint_as_float(ra[4 * i + 2]), a3 = __uint_as_float(ra[4 * i + 3]);
-                                float g0 = __uint_as_float(rg[4 * i]), g1 = __uint_as_float(rg[4 * i + 1]);
-                                float g2 = __uint_as_float(rg[4 * i + 2]), g3 = __uint_as_float(rg[4 * i + 3]);
+                                tc::f32x2 a01 = tc::pk2u(ra[4 * i], ra[4 * i + 1]), a23 = tc::pk2u(ra[4 * i + 2], ra[4 * i + 3]);
+                                tc::f32x2 g01 = tc::pk2u(rg[4 * i], rg[4 * i + 1]), g23 = tc::pk2u(rg[4 * i + 2], rg[4 * i + 3]);
                                 if (p.ln_u) {
                                     const float4 ua = reinterpret_cast<const float4*>(su + cc)[i];
                                     const float4 ug = reinterpret_cast<const float4*>(su + half_bn + cc)[i];
-                                    a0 = fmaf(ln_rstd, a0, fmaf(ln_rm, ua.x, ba.x));
-                                    a1 = fmaf(ln_rstd, a1, fmaf(ln_rm, ua.y, ba.y));
-                                    a2 = fmaf(ln_rstd, a2, fmaf(ln_rm, ua.z, ba.z));
-                                    a3 = fmaf(ln_rstd, a3, fmaf(ln_rm, ua.w, ba.w));
-                                    g0 = fmaf(ln_rstd, g0, fmaf(ln_rm, ug.x, bg.x));
-                                    g1 = fmaf(ln_rstd, g1, fmaf(ln_rm, ug.y, bg.y));
-                                    g2 = fmaf(ln_rstd, g2, fmaf(ln_rm, ug.z, bg.z));
-                                    g3 = fmaf(ln_rstd, g3, fmaf(ln_rm, ug.w, bg.w));
+                                    a01 = tc::fma2(rstd2, a01, tc::fma2(rm2, tc::pk2(ua.x, ua.y), tc::pk2(ba.x, ba.y)));
+                                    a23 = tc::fma2(rstd2, a23, tc::fma2(rm2, tc::pk2(ua.z, ua.w), tc::pk2(ba.z, ba.w)));
+                                    g01 = tc::fma2(rstd2, g01, tc::fma2(rm2, tc::pk2(ug.x, ug.y), tc::pk2(bg.x, bg.y)));
+                                    g23 = tc::fma2(rstd2, g23, tc::fma2(rm2, tc::pk2(ug.z, ug.w), tc::pk2(bg.z, bg.w)));
                                 } else {
-                                    a0 += ba.x, a1 += ba.y, a2 += ba.z, a3 += ba.w;
-                                    g0 += bg.x, g1 += bg.y, g2 += bg.z, g3 += bg.w;
+                                    a01 = tc::add2(a01, tc::pk2(ba.x, ba.y));
+                                    a23 = tc::add2(a23, tc::pk2(ba.z, ba.w));
+                                    g01 = tc::add2(g01, tc::pk2(bg.x, bg.y));
+                                    g23 = tc::add2(g23, tc::pk2(bg.z, bg.w));
                                 }
-                                const __half2 h0 = __floats2half2_rn(tc::geglu_mul(a0, g0), tc::geglu_mul(a1, g1));
-                                const __half2 h1 = __floats2half2_rn(tc::geglu_mul(a2, g2), tc::geglu_mul(a3, g3));
-                                pk[h16 * 8 + 2 * i] = *reinterpret_cast<const uint32_t*>(&h0);
-                                pk[h16 * 8 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+                                pk[h16 * 8 + 2 * i] = tc::h2_from_f2(tc::geglu_mul2(a01, g01));
+                                pk[h16 * 8 + 2 * i + 1] = tc::h2_from_f2(tc::geglu_mul2(a23, g23));
                             }
                         }
                     }
-                    // the previous TMA store must have drained the staging box before it is overwritten
-                    if (store_leader) tc::bulk_wait_group_read<0>();
+                    // two staging boxes in rotation: only the store issued two chunks ago must have drained this one
+                    uint8_t* stg_b = stg + (n_stores & 1u) * 16384u;
+                    const uint32_t stg_row_b = stg_row + (n_stores & 1u) * 16384u;
+                    ++n_stores;
+                    if (store_leader) tc::bulk_wait_group_read<1>();
                     if (warp_box) __syncwarp();
                     else if (cg == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
                     else asm volatile("bar.sync 3, 128;" ::: "memory");
                     if (!(dbg & 16))
 #pragma unroll
                     for (int hh = 0; hh < 4; ++hh) {
-                        const uint32_t dst = stg_row + ((((uint32_t)hh) ^ stg_swz) << 4);
+                        const uint32_t dst = stg_row_b + ((((uint32_t)hh) ^ stg_swz) << 4);
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * hh]),
                                      "r"(pk[4 * hh + 1]), "r"(pk[4 * hh + 2]), "r"(pk[4 * hh + 3])
                                      : "memory");
@@ -630,14 +628,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     if (store_leader && !(dbg & 1)) {
                         if (warp_box) {
                             if (warp_rows_in_tile) {
-                                tc::tma_store_4d(stg, &p.tmOw, nt * width + c, x0 + wx, y0 + wy, n0 + wn);
+                                tc::tma_store_4d(stg_b, &p.tmOw, nt * width + c, x0 + wx, y0 + wy, n0 + wn);
                                 tc::bulk_commit_group();
                             }
                         } else {
-                            tc::tma_store_4d(stg, &p.tmO, nt * width + c, x0, y0, n0);
+                            tc::tma_store_4d(stg_b, &p.tmO, nt * width + c, x0, y0, n0);
                             tc::bulk_commit_group();
                         }
                     }
+                }
+                float rs_sum = 0.f, rs_sq = 0.f;
+                if (kEpi == 0 && p.row_stats) {
+                    float s0, s1, q0, q1;
+                    tc::unpk2(rs_sum2, s0, s1);
+                    tc::unpk2(rs_sq2, q0, q1);
+                    rs_sum = s0 + s1;
+                    rs_sq = q0 + q1;
                 }
                 if (kEpi == 0 && p.row_stats) {
                     // one slot per N tile: group 1 hands {sum, sumsq} of its columns to the warp of group 0 that owns
@@ -795,6 +801,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         }
     }
 #undef TC_DECODE_TILE
+#undef TC_TILE_NT
 
     if (p.tma_store && warp >= 2 && lane == 0) tc::bulk_wait_group<0>();
     tc::tc_fence_before();
@@ -1035,7 +1042,7 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
     }
     const int stage_bytes = kAStageBytes + (pair ? BN / 2 : BN) * 128;
     // alignment slack, barriers, epilogue vectors, store staging, identity tile, row-statistics hand-over
-    const int kFixedSmem = 1024 + 512 + 4096 + 1024 + 16384 + 8192 + 2048;
+    const int kFixedSmem = 1024 + 512 + 4096 + 1024 + 32768 + 8192 + 2048;
     const int smem_budget = 227 * 1024 - kFixedSmem;
     int stages = smem_budget / stage_bytes;
     if (stages > 8) stages = 8;
@@ -1073,16 +1080,24 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
             }
         attr_set = true;
     }
-    int grid;
-    if (pair) {
-        int units = sm_count() / 2;
-        if (pair_tiles < units) units = (int)pair_tiles;
-        grid = 2 * units;
-    } else {
-        const long long total_tiles = (long long)p.tiles_m * p.tiles_nn;
-        grid = sm_count();
-        if (total_tiles < grid) grid = (int)total_tiles;
+    int units = pair ? sm_count() / 2 : sm_count();
+    {
+        const long long total_units = pair ? pair_tiles : (long long)p.tiles_m * p.tiles_nn;
+        if (total_units < units) units = (int)total_units;
+        // N-tile-fastest raster (see TC_DECODE_TILE).  With resident weights the unit count must be a multiple of tiles_nn
+        // (then unit u keeps N tile u % tiles_nn for its whole life); give up at most ~4 % of the SMs for that.
+        static const char* raster_env = getenv("TC_GEMM_RASTER");   // "0" keeps the N-major order (A/B testing)
+        if (p.tiles_nn > 1 && total_units > units && !(raster_env && raster_env[0] == '0')) {
+            const int rounded = units - units % p.tiles_nn;
+            if (rounded > 0 && (units - rounded) * 25 <= units) {
+                units = rounded;
+                p.raster = 1;
+            } else if (!p.b_resident) {
+                p.raster = 1;
+            }
+        }
     }
+    const int grid = pair ? 2 * units : units;
     launch(kernels[pair ? 1 : 0][epi], dim3(grid), dim3(kThreads), smem_bytes, stream, pair ? 2 : 1, p);
     count_launch();
     TC_CHECK_LAUNCH("tc_gemm_kernel launch");
