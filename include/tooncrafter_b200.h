@@ -198,6 +198,13 @@ int tc_small_linear(const float* x, int B, int K, const void* w, const float* bi
 int tc_ddim_step(const void* e_c, const void* e_uc, const float* x, const float* noise, float* x_prev,
                  float* pred_x0, const float* coef, int B, long long n, double* ws, void* stream);
 
+/* Three-way guidance of the multi-condition sampler (lvdm/models/samplers/ddim_multiplecond.py:214-234):
+ *   v = e_uc + cfg_img*(e_img - e_uc) + s*(e_c - e_img)   (fp16 arithmetic, one rounding per torch op, left to right)
+ * followed by the same guidance rescale against std(e_c) and the same v -> (eps, x0) -> x_prev update as tc_ddim_step.
+ * coef holds 9 floats: the 8 of tc_ddim_step and cfg_img. */
+int tc_ddim_step3(const void* e_c, const void* e_uc, const void* e_img, const float* x, const float* noise,
+                  float* x_prev, float* pred_x0, const float* coef, int B, long long n, double* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

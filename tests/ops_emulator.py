@@ -196,10 +196,14 @@ def small_linear(x, w, bias, y, *, silu_in):
     y.copy_(F.linear(xi, w.float(), None if bias is None else bias.float()).to(y.dtype))
 
 
-def ddim_step(e_c, e_uc, x, noise, x_prev, pred_x0, coef, ws, *, B, n):
-    s, phi, sqrt_ac, sqrt_1mac, rescale, sqrt_aprev, dir_coef, sigma = [float(v) for v in coef]
+def ddim_step(e_c, e_uc, x, noise, x_prev, pred_x0, coef, ws, *, B, n, e_img=None):
+    s, phi, sqrt_ac, sqrt_1mac, rescale, sqrt_aprev, dir_coef, sigma = [float(v) for v in coef[:8]]
     ec, eu = e_c.reshape(B, n), e_uc.reshape(B, n)
-    v = eu + s * (ec - eu)                               # half arithmetic, one rounding per op
+    if e_img is None:
+        v = eu + s * (ec - eu)                           # half arithmetic, one rounding per op
+    else:
+        ei = e_img.reshape(B, n)
+        v = eu + float(coef[8]) * (ei - eu) + s * (ec - ei)
     if phi > 0:
         ratio = ec.float().std(dim=1, keepdim=True).half() / v.float().std(dim=1, keepdim=True).half()
         v = phi * (v * ratio) + (1 - phi) * v
@@ -211,9 +215,13 @@ def ddim_step(e_c, e_uc, x, noise, x_prev, pred_x0, coef, ws, *, B, n):
     x_prev.reshape(B, n).copy_(sqrt_aprev * x0 + dir_coef * eps + sigma * nz)
 
 
+def ddim_step3(e_c, e_uc, e_img, x, noise, x_prev, pred_x0, coef, ws, *, B, n):
+    ddim_step(e_c, e_uc, x, noise, x_prev, pred_x0, coef, ws, B=B, n=n, e_img=e_img)
+
+
 _TABLE = {f.__name__: f for f in (conv_gemm, groupnorm, row_stats, layernorm, attention, temporal_attention, softmax_rows,
                                   ncthw_to_cl, cl_to_ncthw, upsample2x, phase_split2, copy2d, add2d, time_embed,
-                                  small_linear, ddim_step, gelu2d)}
+                                  small_linear, ddim_step, ddim_step3, gelu2d)}
 
 
 def executor(fn, args, kw):

@@ -248,3 +248,76 @@ def test_general_sampler_path_and_decode_first_stage():
     img = m.decode_first_stage(samples, ref_context=ref_ctx)
     assert tuple(img.shape) == (1, 3, TINY_T, 8 * TINY_LATENT_HW[0], 8 * TINY_LATENT_HW[1])
     assert torch.isfinite(img).all()
+
+
+def test_multicond_sampler_fused_path_matches_reference_golden():
+    """DDIMSampler_multicond (ddim_multiplecond.py:214-234) on the fused B200 path — the three guidance branches as ONE
+    B = 3 UNet program per step + tc_ddim_step3 — vs the reference's own 4-step sample (golden) with the autocast oracle
+    as yardstick, and vs the general three-pass path on the same GPU."""
+    from make_golden_multicond import CFG_IMG, multicond_inputs
+    from oracle import ddim_oracle, unet_oracle
+    from tooncrafter_b200 import layout
+    from tooncrafter_b200.sampler import DDIMSamplerMultiCond
+    import tooncrafter_b200.sampler as smod
+    _no_tf32()
+    m = _tiny_model()
+    gi = multicond_inputs()
+    to = lambda c: {k: [t.to(DEV) for t in v] for k, v in c.items()}
+    cond, uncond, uimg = to(gi["cond"]), to(gi["uncond"]), to(gi["uncond_img"])
+    x_T, fs = gi["x_T"].to(DEV), gi["fs"].to(DEV)
+    noises = [n.to(DEV) for n in gi["noises"]]
+    real_randn = torch.randn
+
+    def run(sampler):
+        it = iter(noises)
+        smod.torch.randn = lambda *a, **k: next(it)
+        try:
+            out, _ = sampler.sample(S=gi["S"], batch_size=1, shape=list(x_T.shape[1:]), conditioning=cond,
+                                    unconditional_conditioning=uncond, eta=1.0, unconditional_guidance_scale=7.5,
+                                    cfg_img=CFG_IMG, x_T=x_T, fs=fs, timestep_spacing="uniform_trailing",
+                                    guidance_rescale=0.7, verbose=False, unconditional_conditioning_img_nonetext=uimg)
+        finally:
+            smod.torch.randn = real_randn
+        return out
+
+    s = DDIMSamplerMultiCond(m)
+    fused = run(s)
+    plan_keys = list(m.model.diffusion_model._engine._plans.keys())
+    assert any(k[0] == 3 for k in plan_keys), f"the fused multi-cond path must batch the 3 branches (plans: {plan_keys})"
+
+    class General(DDIMSamplerMultiCond):
+        def _fast_path_ok(self, *a, **k):
+            return False
+    general = run(General(m))
+
+    # yardstick: the reference algorithm (oracle) under autocast with the three-way combine
+    sd = {k: v for k, v in m.state_dict().items()}
+    ulay = layout.unet_layout(TINY_UNET)
+    sched = ddim_oracle.model_schedule()
+    tab = ddim_oracle.ddim_tables(sched, gi["S"], 1.0)
+
+    def oracle_sample(autocast):
+        x = x_T
+        for i, step in enumerate(np.flip(tab["timesteps"])):
+            index = gi["S"] - i - 1
+            ts = torch.full((1,), int(step), dtype=torch.long, device=DEV)
+            es = []
+            for c in (cond, uncond, uimg):
+                xc = torch.cat([x] + c["c_concat"], 1)
+                with torch.autocast("cuda", dtype=torch.float16, enabled=autocast):
+                    es.append(unet_oracle.unet_forward(sd, ulay, xc, ts, torch.cat(c["c_crossattn"], 1), fs,
+                                                       "model.diffusion_model."))
+            e_c, e_uc, e_img = es
+            v = e_uc + CFG_IMG * (e_img - e_uc) + 7.5 * (e_c - e_img)
+            v = ddim_oracle.rescale_noise_cfg(v, e_c, 0.7).float()
+            co = ddim_oracle.step_coefficients(sched, tab, index)
+            eps = co["sqrt_ac"] * v + co["sqrt_1mac"] * x
+            x0 = (co["sqrt_ac"] * x - co["sqrt_1mac"] * v) * co["rescale"]
+            x = co["sqrt_aprev"] * x0 + co["dir_coef"] * eps + co["sigma"] * noises[i]
+        return x
+
+    x32, x16 = oracle_sample(False), oracle_sample(True)
+    gold = torch.from_numpy(np.load(HERE / "golden" / "multicond_tiny.npz")["ddim_samples"])
+    assert (x32.cpu() - gold).abs().max().item() < 5e-3, "fp32 oracle disagrees with the reference's multi-cond sample"
+    _report("multi-cond 4-step sample (fused, B = 3 program)", fused, gold, x16)
+    _report("multi-cond 4-step sample (general path)", general, gold, x16)

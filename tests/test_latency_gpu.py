@@ -1,6 +1,9 @@
 """Latency mode: two GPUs share one clip, each evaluates one classifier-free-guidance branch per DDIM step
 and the predictions are all-gathered.  The result must equal the single-GPU fused path (same algorithm, B = 1 + B = 1
-instead of one B = 2 forward).  Needs 2 GPUs: skipped on the single-GPU test box, run with `gpurun --gpus 2`."""
+instead of one B = 2 forward).  The NCCL variant needs 2 GPUs (skipped on a single-GPU box, run with `gpurun --gpus 2`);
+the single-GPU variant runs the SAME two-rank protocol with both ranks time-sharing cuda:0 over gloo (collectives staged
+through host memory), so the pair logic — branch split, per-step exchange, state synchronisation — is exercised wherever
+the GPU tests run."""
 import os
 import sys
 from pathlib import Path
@@ -13,12 +16,15 @@ sys.path.insert(0, str(HERE))
 sys.path.insert(0, str(HERE / "golden"))
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, one_gpu=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
-    torch.cuda.set_device(rank)
-    dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", device_id=dev)
+    dev = torch.device("cuda", 0 if one_gpu else rank)
+    torch.cuda.set_device(dev)
+    if one_gpu:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    else:
+        dist.init_process_group("nccl", device_id=dev)
     from make_golden import SEED, golden_inputs
     from tiny_config import model_config
     from tooncrafter_b200 import diffusion, synthetic
@@ -39,8 +45,12 @@ def _worker(rank, world, port, out):
     s = DDIMSampler(m)
     s.latency_group = group
     lat, _ = s.sample(**kw)
-    both = [torch.empty_like(lat) for _ in range(world)]
-    dist.all_gather(both, lat)
+    both = [torch.empty_like(lat.cpu()) for _ in range(world)]
+    if one_gpu:
+        dist.all_gather(both, lat.cpu())
+    else:
+        both = [torch.empty_like(lat) for _ in range(world)]
+        dist.all_gather(both, lat)
     if rank == 0:
         torch.manual_seed(1234)               # pair-rank 0's stream is the one the pair used
         ref, _ = DDIMSampler(m).sample(**kw)
@@ -50,14 +60,25 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _free_port():
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
 @pytest.mark.gpu
-def test_latency_mode_matches_single_gpu_fused_path():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("latency mode pairs two GPUs")
+@pytest.mark.parametrize("one_gpu", [True, False], ids=["two_ranks_on_one_gpu_gloo", "two_gpus_nccl"])
+def test_latency_mode_matches_single_gpu_fused_path(one_gpu):
+    if not one_gpu and torch.cuda.device_count() < 2:
+        pytest.skip("the NCCL variant pairs two GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, 29533, out)) for r in range(2)]
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out, one_gpu)) for r in range(2)]
     for p in procs:
         p.start()
     res = out.get(timeout=600)

@@ -95,6 +95,8 @@ _PROTOTYPES = {
                                   C.c_longlong, C.c_int, C.c_void_p]),
     "tc_ddim_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "tc_ddim_step3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES.keys())

@@ -135,9 +135,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_cons
         tc::mbar_init(bar_q, 1);
         for (int i = 0; i < kStages; ++i) {
             tc::mbar_init(&k_full[i], 1);
-            tc::mbar_init(&k_free[i], 1);
+            tc::mbar_init(&k_free[i], (uint32_t)ntiles);   // one tcgen05.commit per query tile releases a ring slot
             tc::mbar_init(&v_full[i], 1);
-            tc::mbar_init(&v_free[i], 1);
+            tc::mbar_init(&v_free[i], (uint32_t)ntiles);
         }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&s_full[i], 1);
@@ -207,47 +207,67 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_cons
         tc::tc_fence_after();
         if (tc::elect_one()) {
             const int nk = block_nk(0);
-            for (int w = 0; w < ntiles; ++w) issue_s(w, 0, nk);
-            tc::umma_commit(&k_free[0]);
+            for (int w = 0; w < ntiles; ++w) {
+                issue_s(w, 0, nk);
+                tc::umma_commit(&k_free[0]);          // one arrival per query tile (the barrier counts ntiles)
+            }
         }
         __syncwarp();
-        int st = 0;
-        uint32_t ph = 0;
-        for (int g = 0; g < G; ++g) {
-            const int nk = block_nk(g);
-            // ---- S of the NEXT block as soon as the softmax warps have pulled this block's S into registers
-            if (g + 1 < G) {
-                const int st1 = (st + 1 == kStages) ? 0 : st + 1;
-                const uint32_t ph1 = (st + 1 == kStages) ? (ph ^ 1u) : ph;
-                const int nk1 = block_nk(g + 1);
-                tc::mbar_wait(&k_full[st1], ph1);
-                for (int w = 0; w < ntiles; ++w) {
-                    tc::mbar_wait(&s_free[w], (uint32_t)(g & 1));
-                    tc::tc_fence_after();
-                    if (tc::elect_one()) {
-                        issue_s(w, st1, nk1);
-                        if (w == ntiles - 1) tc::umma_commit(&k_free[st1]);
+        // Event-driven issue: the two query tiles are independent state machines
+        //     [S_w(g+1) once the softmax warps hold S_w(g) in registers]  ->  [O_w += P_w(g) V(g) once P_w(g) is in TMEM]
+        // polled round-robin with non-blocking barrier tests.  Issuing in a fixed order (tile 0 then tile 1) locks the two
+        // softmax warpgroups into the same phase — both in their MUFU-bound exponentials, then both idle on the XU while
+        // they wait for each other's MMAs (measured: 2836 cycles per key block instead of the 2048 the MUFU allows).
+        int gw[2] = {0, ntiles > 1 ? 0 : G};     // block whose PV is next, per tile
+        bool need_s[2] = {true, true};           // state: next action of the tile is S(g + 1)
+        const long long t_start = clock64();
+        while (gw[0] < G || gw[1] < G) {
+            if (clock64() - t_start > 20000000000LL) {   // ~10 s: a protocol bug traps instead of hanging the GPU
+                if (tc::elect_one()) printf("tc_attn3: MMA issuer timeout (block %d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z);
+                __trap();
+            }
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const int g = gw[w];
+                if (g >= G) continue;
+                if (need_s[w]) {
+                    if (g + 1 >= G) {
+                        need_s[w] = false;
+                    } else {
+                        const int st1 = (g + 1) % kStages;
+                        const uint32_t ph1 = (uint32_t)(((g + 1) / kStages) & 1);
+                        if (tc::mbar_try_wait(&s_free[w], (uint32_t)(g & 1)) && tc::mbar_try_wait(&k_full[st1], ph1)) {
+                            tc::tc_fence_after();
+                            if (tc::elect_one()) {
+                                issue_s(w, st1, block_nk(g + 1));
+                                tc::umma_commit(&k_free[st1]);
+                            }
+                            __syncwarp();
+                            need_s[w] = false;
+                        }
                     }
-                    __syncwarp();
+                } else {
+                    const int st = g % kStages;
+                    const uint32_t ph = (uint32_t)((g / kStages) & 1);
+                    if (tc::mbar_try_wait(&p_ready[w], (uint32_t)(g & 1)) && tc::mbar_try_wait(&v_full[st], ph)) {
+                        tc::tc_fence_after();
+                        if (tc::elect_one()) {
+                            const int nk = block_nk(g);
+                            const uint32_t idesc_o = tc::umma_idesc_f16(128, 64, 0, 1);   // B (= V tile [keys][64]) MN-major
+                            const uint64_t vd = tc::umma_desc_sw128(sV_a + (uint32_t)st * kTileBytes);
+                            for (int t = 0; t < nk / 16; ++t)
+                                tc::umma_f16_ts(tmem_base + kTmemO + (uint32_t)w * 64,
+                                                tmem_base + kTmemP + (uint32_t)w * 64 + (uint32_t)(t * 8), vd + (uint64_t)(t * 128),
+                                                idesc_o, (g != 0 || t != 0) ? 1u : 0u);
+                            tc::umma_commit(&o_full[w]);
+                            tc::umma_commit(&v_free[st]);
+                        }
+                        __syncwarp();
+                        gw[w] = g + 1;
+                        need_s[w] = true;
+                    }
                 }
             }
-            // ---- O_w += P_w V for this block (P from tensor memory)
-            tc::mbar_wait(&v_full[st], ph);
-            for (int w = 0; w < ntiles; ++w) {
-                tc::mbar_wait(&p_ready[w], (uint32_t)(g & 1));
-                tc::tc_fence_after();
-                if (tc::elect_one()) {
-                    const uint32_t idesc_o = tc::umma_idesc_f16(128, 64, 0, 1);   // B (= V tile [keys][64]) MN-major
-                    const uint64_t vd = tc::umma_desc_sw128(sV_a + (uint32_t)st * kTileBytes);
-                    for (int t = 0; t < nk / 16; ++t)
-                        tc::umma_f16_ts(tmem_base + kTmemO + (uint32_t)w * 64, tmem_base + kTmemP + (uint32_t)w * 64 + (uint32_t)(t * 8),
-                                        vd + (uint64_t)(t * 128), idesc_o, (g != 0 || t != 0) ? 1u : 0u);
-                    tc::umma_commit(&o_full[w]);
-                    if (w == ntiles - 1) tc::umma_commit(&v_free[st]);
-                }
-                __syncwarp();
-            }
-            if (++st == kStages) { st = 0; ph ^= 1u; }
         }
     } else if ((warp >> 2) < ntiles) {
         // ------------------------------------------------------------------------------ softmax warpgroups
@@ -291,24 +311,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_cons
             // ---- lazy rescale: keep the old reference maximum unless the row maximum grew by more than 2^8
             const bool grow = (m_new - m_run) * c > kRescaleThreshold;    // first block: (x - -inf) = +inf -> true
             const float m_use = grow ? m_new : m_run;
-            if (g > 0) {
-                tc::mbar_wait(&o_full[w], (uint32_t)((g - 1) & 1));       // PV of the previous block retired: P and O are ours
-                tc::tc_fence_after();
-                if (__any_sync(0xffffffffu, grow)) {
-                    const float alpha = ex2((m_run - m_use) * c);          // 1 for the rows that keep their maximum
-                    l_run *= alpha;
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        uint32_t r[16];
-                        tc::tmem_ld16(tmem_o + (uint32_t)(cc * 16), r);
-                        tc::tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                        tc::tmem_st16(tmem_o + (uint32_t)(cc * 16), r);
-                    }
-                    tc::tmem_st_wait();
-                }
-            }
+            const float alpha = ex2((m_run - m_use) * c);                  // 1 for the rows that keep their maximum
+            const bool any_grow = g > 0 && __any_sync(0xffffffffu, grow);
             m_run = m_use;
             const float nm = -m_use * c;
             const u64 nm2 = pack2(nm, nm);
@@ -330,6 +334,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_cons
                 if (j & 1) sum_b = add2(sum_b, pack2(e0, e1));
                 else sum_a = add2(sum_a, pack2(e0, e1));
                 pk[j] = pack_h2(e0, e1);
+            }
+            // Only now must the previous block's PV MMA have retired (it reads P and accumulates into O): waiting here,
+            // after the ~1000-cycle exponential phase, instead of before it took a 5 % long-scoreboard stall off the
+            // critical path (profiles/r02_ncu_attn3_2560_first.txt).
+            if (g > 0) {
+                tc::mbar_wait(&o_full[w], (uint32_t)((g - 1) & 1));
+                tc::tc_fence_after();
+                if (any_grow) {
+                    l_run *= alpha;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        uint32_t r[16];
+                        tc::tmem_ld16(tmem_o + (uint32_t)(cc * 16), r);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                        tc::tmem_st16(tmem_o + (uint32_t)(cc * 16), r);
+                    }
+                }
             }
             tc::tmem_st32(tmem_p, &pk[0]);
             tc::tmem_st32(tmem_p + 32, &pk[32]);

@@ -214,19 +214,38 @@ __device__ __forceinline__ __half cfg_combine(__half ec, __half euc, float s) {
     return __float2half_rn(__half2float(euc) + __half2float(m));
 }
 
+// three-way guidance of the multi-condition sampler (ddim_multiplecond.py:229):
+//   e_uc + cfg_img * (e_img - e_uc) + s * (e_c - e_img), every torch op rounding to half, left to right
+__device__ __forceinline__ __half cfg_combine3(__half ec, __half euc, __half eimg, float s, float cfg_img) {
+    const __half d1 = __float2half_rn(__half2float(eimg) - __half2float(euc));
+    const __half m1 = __float2half_rn(cfg_img * __half2float(d1));
+    const __half a1 = __float2half_rn(__half2float(euc) + __half2float(m1));
+    const __half d2 = __float2half_rn(__half2float(ec) - __half2float(eimg));
+    const __half m2 = __float2half_rn(s * __half2float(d2));
+    return __float2half_rn(__half2float(a1) + __half2float(m2));
+}
+// e_img == nullptr: the two-way combine of ddim.py:226; coef[8] (cfg_img) is only read for the three-way form
+__device__ __forceinline__ __half cfg_any(const __half* ec, const __half* eu, const __half* ei, long long i, float s,
+                                          float cfg_img) {
+    return ei ? cfg_combine3(ec[i], eu[i], ei[i], s, cfg_img) : cfg_combine(ec[i], eu[i], s);
+}
+
 // partial sums for std(e_c) and std(v): ws[b][blk][4] = {sum_ec, sumsq_ec, sum_v, sumsq_v} (double)
 __global__ void ddim_reduce_kernel(const __half* __restrict__ e_c, const __half* __restrict__ e_uc,
-                                   const float* __restrict__ coef, long long n, double* __restrict__ ws) {
+                                   const __half* __restrict__ e_img, const float* __restrict__ coef, long long n,
+                                   double* __restrict__ ws) {
     tc::pdl_wait();   // no early launch_dependents: waiting successor CTAs would squat on this kernel's SM slots
     const int b = blockIdx.y;
     const float s = coef[0];
+    const float cfg_img = e_img ? coef[8] : 0.f;
     const __half* ec = e_c + (long long)b * n;
     const __half* eu = e_uc + (long long)b * n;
+    const __half* ei = e_img ? e_img + (long long)b * n : nullptr;
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
         const float c = __half2float(ec[i]);
-        const float v = __half2float(cfg_combine(ec[i], eu[i], s));
+        const float v = __half2float(cfg_any(ec, eu, ei, i, s, cfg_img));
         a0 += c;
         a1 += (double)c * c;
         a2 += v;
@@ -256,7 +275,7 @@ __global__ void ddim_reduce_kernel(const __half* __restrict__ e_c, const __half*
 }
 
 __global__ void ddim_update_kernel(const __half* __restrict__ e_c, const __half* __restrict__ e_uc,
-                                   const float* __restrict__ x, const float* __restrict__ noise,
+                                   const __half* __restrict__ e_img, const float* __restrict__ x, const float* __restrict__ noise,
                                    float* __restrict__ x_prev, float* __restrict__ pred_x0,
                                    const float* __restrict__ coef, long long n, const double* __restrict__ ws,
                                    int nblk) {
@@ -284,9 +303,11 @@ __global__ void ddim_update_kernel(const __half* __restrict__ e_c, const __half*
     __syncthreads();
     const float ratio = s_ratio;
     const long long off = (long long)b * n;
+    const float cfg_img = e_img ? coef[8] : 0.f;
+    const __half* ei = e_img ? e_img + off : nullptr;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
-        __half vh = cfg_combine(e_c[off + i], e_uc[off + i], s);
+        __half vh = cfg_any(e_c + off, e_uc + off, ei, i, s, cfg_img);
         if (phi > 0.f) {
             const __half resc = __float2half_rn(__half2float(vh) * ratio);
             const __half t1 = __float2half_rn(phi * __half2float(resc));
@@ -437,20 +458,33 @@ extern "C" int tc_small_linear(const float* x, int B, int K, const void* w, cons
     return TC_OK;
 }
 
-extern "C" int tc_ddim_step(const void* e_c, const void* e_uc, const float* x, const float* noise, float* x_prev,
-                            float* pred_x0, const float* coef, int B, long long n, double* ws, void* stream_v) {
-    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-    TC_CHECK_ARG(e_c && e_uc && x && noise && x_prev && pred_x0 && coef && ws && B > 0 && n > 1,
-                 "tc_ddim_step: bad arguments");
-    tc_host::launch(ddim_reduce_kernel, dim3(dim3(TC_DDIM_PARTIALS, B)), dim3(256), 0, stream, 1, 
-        reinterpret_cast<const __half*>(e_c), reinterpret_cast<const __half*>(e_uc), coef, n, ws);
+static int ddim_step_impl(const void* e_c, const void* e_uc, const void* e_img, const float* x, const float* noise,
+                          float* x_prev, float* pred_x0, const float* coef, int B, long long n, double* ws,
+                          cudaStream_t stream) {
+    const __half* ei = reinterpret_cast<const __half*>(e_img);
+    tc_host::launch(ddim_reduce_kernel, dim3(dim3(TC_DDIM_PARTIALS, B)), dim3(256), 0, stream, 1,
+                    reinterpret_cast<const __half*>(e_c), reinterpret_cast<const __half*>(e_uc), ei, coef, n, ws);
     count_launch();
     TC_CHECK_LAUNCH("ddim_reduce_kernel");
     int g = grid_for(n, 256, 4 * sm_count());
     tc_host::launch(ddim_update_kernel, dim3(dim3(g, B)), dim3(256), 0, stream, 1, reinterpret_cast<const __half*>(e_c),
-                                                       reinterpret_cast<const __half*>(e_uc), x, noise, x_prev,
-                                                       pred_x0, coef, n, ws, TC_DDIM_PARTIALS);
+                    reinterpret_cast<const __half*>(e_uc), ei, x, noise, x_prev, pred_x0, coef, n, ws, TC_DDIM_PARTIALS);
     count_launch();
     TC_CHECK_LAUNCH("ddim_update_kernel");
     return TC_OK;
+}
+
+extern "C" int tc_ddim_step(const void* e_c, const void* e_uc, const float* x, const float* noise, float* x_prev,
+                            float* pred_x0, const float* coef, int B, long long n, double* ws, void* stream_v) {
+    TC_CHECK_ARG(e_c && e_uc && x && noise && x_prev && pred_x0 && coef && ws && B > 0 && n > 1,
+                 "tc_ddim_step: bad arguments");
+    return ddim_step_impl(e_c, e_uc, nullptr, x, noise, x_prev, pred_x0, coef, B, n, ws, reinterpret_cast<cudaStream_t>(stream_v));
+}
+
+extern "C" int tc_ddim_step3(const void* e_c, const void* e_uc, const void* e_img, const float* x, const float* noise,
+                             float* x_prev, float* pred_x0, const float* coef, int B, long long n, double* ws,
+                             void* stream_v) {
+    TC_CHECK_ARG(e_c && e_uc && e_img && x && noise && x_prev && pred_x0 && coef && ws && B > 0 && n > 1,
+                 "tc_ddim_step3: bad arguments");
+    return ddim_step_impl(e_c, e_uc, e_img, x, noise, x_prev, pred_x0, coef, B, n, ws, reinterpret_cast<cudaStream_t>(stream_v));
 }

@@ -61,6 +61,7 @@ struct alignas(64) GemmKParams {
     int tiles_m, tiles_nn;          // tiles along M and along N
     int BN;
     int raster;                     // tile order, see TC_DECODE_TILE
+    int stage_bufs;                 // 1 or 2 output staging boxes (2: short-K launches, whose epilogue is the bottleneck)
     int n_cols;
     int stages;
     uint32_t a_bytes;  // bytes delivered per A box
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     // output staging for the TMA-store epilogue: one 128-row x 32-column (64 B, 64B-swizzled) box per column group
     uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_epi + 1024) + 1023) & ~uintptr_t(1023));
     // 64 x 64 identity (K-major, 128B-swizzled like a weight tile): the B operand of the residual k-blocks
-    uint8_t* s_eye = s_stage + 32768;                     // two staging boxes (16 KiB each) in rotation
+    uint8_t* s_eye = s_stage + (size_t)p.stage_bufs * 16384;   // one or two staging boxes (16 KiB each) in rotation
     // producer-side row statistics: column group 1 hands its partials to group 0 (two buffers by tile parity)
     float2* s_rs = reinterpret_cast<float2*>(s_eye + 8192);
 
@@ -606,10 +607,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                         }
                     }
                     // two staging boxes in rotation: only the store issued two chunks ago must have drained this one
-                    uint8_t* stg_b = stg + (n_stores & 1u) * 16384u;
-                    const uint32_t stg_row_b = stg_row + (n_stores & 1u) * 16384u;
+                    const uint32_t buf = n_stores & (uint32_t)(p.stage_bufs - 1);
+                    uint8_t* stg_b = stg + buf * 16384u;
+                    const uint32_t stg_row_b = stg_row + buf * 16384u;
                     ++n_stores;
-                    if (store_leader) tc::bulk_wait_group_read<1>();
+                    if (store_leader) {
+                        if (p.stage_bufs == 2) tc::bulk_wait_group_read<1>(); else tc::bulk_wait_group_read<0>();
+                    }
                     if (warp_box) __syncwarp();
                     else if (cg == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
                     else asm volatile("bar.sync 3, 128;" ::: "memory");
@@ -1041,8 +1045,11 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
         }
     }
     const int stage_bytes = kAStageBytes + (pair ? BN / 2 : BN) * 128;
+    // a second staging box pays off where the epilogue bounds the tile time (short K loops); long K loops would rather
+    // have the 16 KiB as operand pipeline depth (conv 320->320 lost 10 % when it went from 5 to 4 stages)
+    p.stage_bufs = (p.tma_store && d->taps * (d->a_C / kBlockK) <= 12) ? 2 : 1;
     // alignment slack, barriers, epilogue vectors, store staging, identity tile, row-statistics hand-over
-    const int kFixedSmem = 1024 + 512 + 4096 + 1024 + 32768 + 8192 + 2048;
+    const int kFixedSmem = 1024 + 512 + 4096 + 1024 + 16384 * p.stage_bufs + 8192 + 2048;
     const int smem_budget = 227 * 1024 - kFixedSmem;
     int stages = smem_budget / stage_bytes;
     if (stages > 8) stages = 8;

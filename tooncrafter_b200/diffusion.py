@@ -124,10 +124,12 @@ class AutoencoderKL(nn.Module):
         return next(self.parameters()).device
 
     def encode(self, x, return_hidden_states=False, **kwargs):
+        from . import runtime
         from .vae_engine import EncoderEngine
+        ex = runtime.TEST_EXECUTOR
         if self._enc_engine is None or not self._enc_engine.matches(self):
-            self._enc_engine = EncoderEngine(self)
-        moments, hidden = self._enc_engine.encode(x)
+            self._enc_engine = EncoderEngine(self, plan_only=ex is not None)
+        moments, hidden = self._enc_engine.encode(x, executor=ex)
         post = DiagonalGaussianDistribution(moments)
         return (post, hidden) if return_hidden_states else post
 
@@ -137,13 +139,15 @@ class AutoencoderKL(nn.Module):
         if len(kwargs) == 0:
             raise NotImplementedError("decode() without ref_context/timesteps never happens on the VideoDecoder path "
                                       "(SURVEY App. C.2)")
+        from . import runtime
+        ex = runtime.TEST_EXECUTOR
         if self._dec_engine is None or not self._dec_engine.matches(self.decoder):
-            self._dec_engine = DecoderEngine(self.decoder)
+            self._dec_engine = DecoderEngine(self.decoder, plan_only=ex is not None)
         ref = kwargs.get("ref_context")
         T = kwargs.get("timesteps") or z.shape[0]
         if z.shape[0] != T:
             raise NotImplementedError("one clip per decode call (the reference mixes clips for B > 1, SURVEY App. C.3)")
-        return self._dec_engine.decode(z.float(), ref).clone()
+        return self._dec_engine.decode(z.float(), ref, executor=ex).clone()
 
 
 class AutoencoderKL_Dualref(AutoencoderKL):

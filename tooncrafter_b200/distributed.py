@@ -83,11 +83,41 @@ def latency_pairs():
     return mine, rank // 2, rank % 2
 
 
+def _device_collectives(group) -> bool:
+    """NCCL moves device tensors directly (NVLink); any other backend (gloo: two ranks time-sharing ONE GPU in the
+    single-GPU test, or CPU tests) is staged through host memory."""
+    return dist.get_backend(group) == "nccl"
+
+
+def pair_broadcast(t: torch.Tensor, src: int, group) -> None:
+    if _device_collectives(group) or t.device.type == "cpu":
+        dist.broadcast(t, src=src, group=group)
+        return
+    h = t.cpu()
+    dist.broadcast(h, src=src, group=group)
+    t.copy_(h)
+
+
+def pair_all_gather(out: torch.Tensor, inp: torch.Tensor, group) -> None:
+    """out[r * n:(r + 1) * n] = inp of pair-rank r (the per-step exchange of latency mode: 2 x 327 KB of fp16)."""
+    if _device_collectives(group) or inp.device.type == "cpu":
+        dist.all_gather_into_tensor(out, inp, group=group)
+        return
+    parts = [torch.empty(inp.shape, dtype=inp.dtype) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(parts, inp.cpu().contiguous(), group=group)
+    out.copy_(torch.cat(parts, 0))
+
+
 def sync_pair_state(x: torch.Tensor, group) -> None:
     """Make the start latent and the CUDA RNG stream of a latency pair identical (pair-rank 0 wins), so that both ranks
     draw the same per-step noise (ddim.py:273) and apply the same update."""
     src = dist.get_global_rank(group, 0)
-    dist.broadcast(x, src=src, group=group)
-    state = torch.cuda.get_rng_state(x.device).to(x.device)
-    dist.broadcast(state, src=src, group=group)
-    torch.cuda.set_rng_state(state.cpu(), x.device)
+    pair_broadcast(x, src, group)
+    state = torch.cuda.get_rng_state(x.device)              # a CPU byte tensor
+    if _device_collectives(group):
+        dstate = state.to(x.device)
+        dist.broadcast(dstate, src=src, group=group)
+        state = dstate.cpu()
+    else:
+        dist.broadcast(state, src=src, group=group)
+    torch.cuda.set_rng_state(state, x.device)

@@ -176,10 +176,12 @@ class UNetModel(nn.Module):
         Extra kwargs are tolerated and ignored exactly like the reference (openaimodel3d.py:548)."""
         if features_adapter is not None:
             raise NotImplementedError("features_adapter is outside the supported hot path")
+        from . import runtime
         from .engine import UNetEngine
+        ex = runtime.TEST_EXECUTOR
         if self._engine is None or not self._engine.matches(self):
-            self._engine = UNetEngine(self)
-        return self._engine.forward(x, timesteps, context, fs).clone()
+            self._engine = UNetEngine(self, plan_only=ex is not None)
+        return self._engine.forward(x, timesteps, context, fs, executor=ex).clone()
 
 
 # ----------------------------------------------------------------------------------------------------- VAE parts

@@ -260,5 +260,13 @@ def ddim_step(e_c, e_uc, x, noise, x_prev, pred_x0, coef, ws, *, B: int, n: int)
                            pred_x0.data_ptr(), coef.data_ptr(), B, n, ws.data_ptr(), _stream()), "tc_ddim_step")
 
 
+def ddim_step3(e_c, e_uc, e_img, x, noise, x_prev, pred_x0, coef, ws, *, B: int, n: int) -> None:
+    """Three-way guidance (text / image-without-text / unconditional) + the update; coef holds 9 floats."""
+    lib = _lib.load()
+    check(lib.tc_ddim_step3(e_c.data_ptr(), e_uc.data_ptr(), e_img.data_ptr(), x.data_ptr(), noise.data_ptr(),
+                            x_prev.data_ptr(), pred_x0.data_ptr(), coef.data_ptr(), B, n, ws.data_ptr(), _stream()),
+          "tc_ddim_step3")
+
+
 def launch_count() -> int:
     return int(_lib.load().tc_launch_count())

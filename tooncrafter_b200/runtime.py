@@ -14,6 +14,12 @@ from typing import Callable, List, Optional
 
 import torch
 
+# TESTS ONLY.  tests/ops_emulator.executor is installed here by host-logic tests that drive the public API (samplers,
+# UNetModel.forward, AutoencoderKL.encode / decode) without a GPU: engines are then built plan-only and their recorded
+# programs are interpreted in PyTorch instead of launched.  The product never sets it; with it unset a CPU module still
+# raises ("CUDA only, no CPU fallback").
+TEST_EXECUTOR: Optional[Callable] = None
+
 
 class Arena:
     """First-fit allocator with coalescing over one device buffer (used only while a program is being built)."""

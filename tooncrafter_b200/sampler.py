@@ -53,7 +53,8 @@ class DDIMSampler(object):
         # guidance branch per rank and all-gathers the two predictions every step
         self.latency_group = None
         # tests only: interpret the engine's recorded programs and the fused update on the PyTorch emulator (no GPU)
-        self._test_executor = None
+        from . import runtime
+        self._test_executor = runtime.TEST_EXECUTOR
         self.model = model
         self.ddpm_num_timesteps = model.num_timesteps
         self.schedule = schedule
@@ -116,7 +117,7 @@ class DDIMSampler(object):
                                   precision=precision, fs=fs, guidance_rescale=guidance_rescale, **kwargs)
 
     def _fast_path_ok(self, cond, uc, cfg_scale, mask, quantize, corrector, noise_dropout, precision, orig_steps,
-                      shape):
+                      shape, kwargs=None):
         m = self.model
         unet = getattr(getattr(m, "model", None), "diffusion_model", None)
         return (m.parameterization == "v" and uc is not None and cfg_scale != 1.0 and isinstance(cond, dict)
@@ -148,10 +149,11 @@ class DDIMSampler(object):
 
         if self._fast_path_ok(cond, unconditional_conditioning, unconditional_guidance_scale, mask,
                               quantize_denoised, score_corrector, noise_dropout, precision,
-                              ddim_use_original_steps, shape):
-            return self._sample_fused(cond, unconditional_conditioning, img, list(time_range), total_steps,
-                                      unconditional_guidance_scale, guidance_rescale, temperature, fs, callback,
-                                      img_callback, log_every_t, intermediates)
+                              ddim_use_original_steps, shape, kwargs):
+            return self._sample_fused(self._guidance_branches(cond, unconditional_conditioning, kwargs), img,
+                                      list(time_range), total_steps, unconditional_guidance_scale, guidance_rescale,
+                                      temperature, fs, callback, img_callback, log_every_t, intermediates,
+                                      cfg_img=self._cfg_img(unconditional_guidance_scale, kwargs))
 
         for i, step in enumerate(time_range):
             index = total_steps - i - 1
@@ -177,6 +179,13 @@ class DDIMSampler(object):
         return img, intermediates
 
     # -------------------------------------------------------------------------------------------- fused fast path
+    def _guidance_branches(self, cond, uc, kwargs):
+        """Conditioning dicts evaluated per step, in the row order of the batched UNet program: [cond, uncond]."""
+        return [cond, uc]
+
+    def _cfg_img(self, cfg_scale, kwargs):
+        return None
+
     def step_coefficients(self, index, cfg_scale, phi, temperature=1.0):
         """The 8 scalars of tc_ddim_step for DDIM index `index`, evaluated in the reference's op order / precision
         (ddim.py:251-254,263-264,271; fp32 torch.full tensors)."""
@@ -191,17 +200,19 @@ class DDIMSampler(object):
                 float(self.model.sqrt_one_minus_alphas_cumprod[t]), rescale, float(a_prev.sqrt()),
                 float((1.0 - a_prev - sigma ** 2).sqrt()), float(sigma) * float(temperature)]
 
-    def _fused_setup(self, cond, uc, shape, steps, cfg_scale, phi, temperature, fs):
+    def _fused_setup(self, cond, uc, shape, steps, cfg_scale, phi, temperature, fs, extra_branches=(), cfg_img=None):
         """Everything of the fused path that is per-`sample()` call: engine / plan lookup, conditioning K/V program,
         concat channels, fps, and the device tables of per-step coefficients.  `steps` = [(ddim index, t), ...] in
-        execution order.  Returns the state `_fused_step` consumes."""
+        execution order.  `extra_branches`: further conditioning dicts batched after [cond, uncond] (the multi-condition
+        sampler's image-without-text branch, with `cfg_img`).  Returns the state `_fused_step` consumes."""
         from .engine import _P
         m = self.model
         dev = m.device
         unet = m.model.diffusion_model
         from .engine import UNetEngine
+        ex = getattr(self, "_test_executor", None)
         if unet._engine is None or not unet._engine.matches(unet):
-            unet._engine = UNetEngine(unet)
+            unet._engine = UNetEngine(unet, plan_only=ex is not None)
         eng = unet._engine
         b, c, T, H, W = shape
         group = getattr(self, "latency_group", None)
@@ -214,11 +225,11 @@ class DDIMSampler(object):
             cc = torch.cat(mine["c_concat"], 1)
             nb = b
         else:
-            ctx = torch.cat([torch.cat(cond["c_crossattn"], 1), torch.cat(uc["c_crossattn"], 1)], 0)
-            cc = torch.cat([torch.cat(cond["c_concat"], 1), torch.cat(uc["c_concat"], 1)], 0)
-            nb = 2 * b
+            branches = [cond, uc, *extra_branches]
+            ctx = torch.cat([torch.cat(c_["c_crossattn"], 1) for c_ in branches], 0)
+            cc = torch.cat([torch.cat(c_["c_concat"], 1) for c_ in branches], 0)
+            nb = len(branches) * b
         plan = eng.plan_for(nb, T, H, W, ctx.shape[1])
-        ex = getattr(self, "_test_executor", None)
         eng.set_context(plan, ctx, ex)                  # always re-run: a new prompt must never see old K/V
         plan.x_in[:, c:].copy_(cc)
         if eng.lay.fs_condition:
@@ -227,8 +238,12 @@ class DDIMSampler(object):
             else:
                 f = torch.as_tensor(fs, device=dev).to(torch.float32).reshape(-1)
                 plan.fs_in.copy_(torch.cat([f.expand(b)] * (nb // b)))
-        st = _P(eng=eng, plan=plan, ex=ex, group=group, b=b, c=c, nb=nb, n=c * T * H * W, dev=dev)
-        st.coef_table = torch.tensor([self.step_coefficients(index, cfg_scale, phi, temperature)
+        st = _P(eng=eng, plan=plan, ex=ex, group=group, b=b, c=c, nb=nb, n=c * T * H * W, dev=dev,
+                three=len(extra_branches) == 1)
+        if len(extra_branches) > 1 or (extra_branches and group is not None):
+            raise NotImplementedError("fused path: at most one extra guidance branch, not in latency mode")
+        tail = [float(cfg_img)] if st.three else []
+        st.coef_table = torch.tensor([self.step_coefficients(index, cfg_scale, phi, temperature) + tail
                                       for index, _ in steps], dtype=torch.float32, device=dev)
         st.t_table = torch.tensor([float(t) for _, t in steps], dtype=torch.float32, device=dev)
         st.ws = torch.empty(4 * b * ops.DDIM_PARTIALS, dtype=torch.float64, device=dev)
@@ -240,30 +255,35 @@ class DDIMSampler(object):
         """One DDIM step (row i of the tables): batched UNet program replay + the fused update.  Writes x_next and
         pred_x0; afterwards st.plan.y_out still holds the two UNet predictions of this step."""
         plan, b, c = st.plan, st.b, st.c
-        plan.x_in[:b, :c].copy_(x)
-        if st.group is None:
-            plan.x_in[b:, :c].copy_(x)
+        for r in range(st.nb // b):                                          # the same latent under every branch
+            plan.x_in[r * b:(r + 1) * b, :c].copy_(x)
         plan.t_in.copy_(st.t_table[i].expand(st.nb))
         if st.ex is None:
             plan.main.replay(st.eng.use_graph)
         else:
             plan.main.run(st.ex)
+        e_img = None
         if st.group is None:
             y = plan.y_out
-            e_c, e_uc = y[:b], y[b:]
+            e_c, e_uc = y[:b], y[b:2 * b]
+            if st.three:
+                e_img = y[2 * b:3 * b]
         else:
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(st.e_all, plan.y_out, group=st.group)   # the step's only exchange (2 x 327 KB)
+            from .distributed import pair_all_gather
+            pair_all_gather(st.e_all, plan.y_out, st.group)                      # the step's only exchange (2 x 327 KB)
             e_c, e_uc = st.e_all[:b], st.e_all[b:]
+        fn, args = ((ops.ddim_step3, (e_c, e_uc, e_img, x, noise, x_next, pred_x0, st.coef_table[i], st.ws)) if st.three
+                    else (ops.ddim_step, (e_c, e_uc, x, noise, x_next, pred_x0, st.coef_table[i], st.ws)))
         if st.ex is None:
-            ops.ddim_step(e_c, e_uc, x, noise, x_next, pred_x0, st.coef_table[i], st.ws, B=b, n=st.n)
+            fn(*args, B=b, n=st.n)
         else:
-            st.ex(ops.ddim_step, (e_c, e_uc, x, noise, x_next, pred_x0, st.coef_table[i], st.ws), dict(B=b, n=st.n))
+            st.ex(fn, args, dict(B=b, n=st.n))
 
-    def _sample_fused(self, cond, uc, img, time_range, total_steps, cfg_scale, phi, temperature, fs, callback,
-                      img_callback, log_every_t, intermediates):
+    def _sample_fused(self, branches, img, time_range, total_steps, cfg_scale, phi, temperature, fs, callback,
+                      img_callback, log_every_t, intermediates, cfg_img=None):
         steps = [(total_steps - i - 1, time_range[i]) for i in range(total_steps)]
-        st = self._fused_setup(cond, uc, tuple(img.shape), steps, cfg_scale, phi, temperature, fs)
+        st = self._fused_setup(branches[0], branches[1], tuple(img.shape), steps, cfg_scale, phi, temperature, fs,
+                               extra_branches=tuple(branches[2:]), cfg_img=cfg_img)
         x = img.to(torch.float32).contiguous().clone()
         x_next = torch.empty_like(x)
         pred_x0 = torch.empty_like(x)
@@ -341,11 +361,25 @@ class DDIMSampler(object):
 
 class DDIMSamplerMultiCond(DDIMSampler):
     """lvdm/models/samplers/ddim_multiplecond.py:10-320 — three-way guidance (text / image-without-text / uncond):
-    v = e_uc + cfg_img * (e_img - e_uc) + s * (e_c - e_img)  (:229-234).  Each term is one pass through the CUDA UNet
-    engine; the update itself follows the general path."""
+    v = e_uc + cfg_img * (e_img - e_uc) + s * (e_c - e_img)  (:229-234).
 
-    def _fast_path_ok(self, *a, **k):
-        return False
+    Fused path (same option set as DDIMSampler's): the three branches run as ONE B = 3b UNet program per step and
+    tc_ddim_step3 does the three-way combine, guidance rescale and update.  Other option combinations take the
+    general path below: three passes through the CUDA UNet engine + torch elementwise plumbing."""
+
+    def _fast_path_ok(self, cond, uc, cfg_scale, mask, quantize, corrector, noise_dropout, precision, orig_steps,
+                      shape, kwargs=None):
+        img_uc = (kwargs or {}).get("unconditional_conditioning_img_nonetext")
+        return (isinstance(img_uc, dict) and self.latency_group is None and
+                super()._fast_path_ok(cond, uc, cfg_scale, mask, quantize, corrector, noise_dropout, precision,
+                                      orig_steps, shape, kwargs))
+
+    def _guidance_branches(self, cond, uc, kwargs):
+        return [cond, uc, kwargs["unconditional_conditioning_img_nonetext"]]
+
+    def _cfg_img(self, cfg_scale, kwargs):
+        v = kwargs.get("cfg_img")
+        return float(cfg_scale if v is None else v)
 
     @torch.no_grad()
     def p_sample_ddim(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,
