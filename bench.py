@@ -221,7 +221,10 @@ def gemm_roofline(model, dev):
 # ---------------------------------------------------------------------------------------------------- CPU arm
 def gemm_traffic():
     """(dram bytes per tc_gemm_kernel launch, provenance) from the committed ncu launch list, or (None, reason)."""
-    p = Path(__file__).resolve().parent / "profiles" / "r01_unet_b2_launches_final.gemm_traffic.json"
+    prof = Path(__file__).resolve().parent / "profiles"
+    p = prof / "r02_unet_b2_launches.gemm_traffic.json"
+    if not p.exists():
+        p = prof / "r01_unet_b2_launches_final.gemm_traffic.json"
     try:
         d = json.loads(p.read_text())
         return float(d["dram_bytes_per_launch"]), f"profiles/{p.name}: {d['launches']} launches, {d['source']}"

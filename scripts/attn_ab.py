@@ -113,10 +113,44 @@ def timing(quick):
             print(f"time {sname:46s} {name:14s}: {ms * 1e3:9.1f} us  {fl / ms / 1e9:7.1f} TF/s", flush=True)
 
 
+def cross_timing():
+    """text (77 keys, shared by the 16 frames of a sample) + image (16 keys per frame) cross attention at the UNet levels"""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    for name, N, L, heads in (("unet L0 cross", 32, 2560, 5), ("unet L1 cross", 32, 640, 10), ("unet L2 cross", 32, 160, 20)):
+        C = heads * 64
+        q = torch.randn(N, L, C, device=DEV).half()
+        kt, vt = torch.randn(2, 77, C, device=DEV).half(), torch.randn(2, 77, C, device=DEV).half()
+        ki, vi = torch.randn(N, 16, C, device=DEV).half(), torch.randn(N, 16, C, device=DEV).half()
+        out = torch.zeros_like(q)
+        segs = [dict(k=kt, v=vt, ldk=C, ldv=C, Lk=77, kv_div=16), dict(k=ki, v=vi, ldk=C, ldv=C, Lk=16)]
+        fn = lambda: ops.attention(q, segs, out, q_batches=N, Lq=L, heads=heads, scale=64 ** -0.5, ldq=C, ldo=C)
+        fl = 4.0 * N * heads * L * 93 * 64
+        for vname, env in (("v2", dict(TC_ATTN_IMPL="v2")), ("resident kv", dict(TC_ATTN_IMPL="v3"))):
+            set_env(env)
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(7):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ts.sort()
+            print(f"time {name:46s} {vname:14s}: {ts[3] * 1e3:9.1f} us  {fl / ts[3] / 1e9:7.1f} TF/s  "
+                  f"{(4.0 * N * L * C) / ts[3] / 1e6:7.0f} GB/s (q + out)", flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--cross-only", action="store_true")
     a = ap.parse_args()
+    ap2 = a
+    if getattr(a, "cross_only", False):
+        cross_timing()
+        sys.exit(0)
     good = parity()
     timing(a.quick)
+    cross_timing()
     print("PARITY_OK" if good else "PARITY_FAILED")

@@ -66,7 +66,8 @@ def main(csv_path, B=2, out=None):
         ks = KERNELS_PER_OP[fn.__name__]
         ms = 0.0; dram = 0.0
         for k in ks:
-            ok = ours[i][0] == k or (k == "row_stats_kernel" and ours[i][0] == "layernorm_kernel")   # older captures
+            ok = (ours[i][0] == k or (k == "row_stats_kernel" and ours[i][0] == "layernorm_kernel")   # older captures
+                  or (k == "tc_attn_kernel" and ours[i][0] in ("tc_attn3_kernel", "tc_attn_xs_kernel")))   # round-2 kernels
             assert ok, (i, ours[i], k)
             ms += ours[i][1]; grid = ours[i][2]; dram += ours[i][3]; i += 1
         d = describe(fn, a, kw); d["ms"] = ms; d["grid"] = grid; d["dram"] = dram

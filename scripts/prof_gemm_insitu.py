@@ -47,9 +47,20 @@ def setup():
 
 if __name__ == "__main__":
     cases = setup()
-    names = sys.argv[1:] or list(cases)
+    modes = [0]
+    args = sys.argv[1:]
+    if args and args[0].startswith("--modes="):
+        # tc_debug_set_gemm_mode bits: 1 = no global / TMA stores, 2 = no epilogue body (mainloop + handshakes only),
+        # 8 = no proxy fence, 16 = no staging stores
+        modes = [int(m) for m in args.pop(0).split("=")[1].split(",")]
+    names = args or list(cases)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
-    for n in names:
+    from tooncrafter_b200 import _lib
+    lib = _lib.load()
+    for n in [(nm, md) for nm in names for md in modes]:
+        n, mode = n
+        _lib.check(lib.tc_debug_set_gemm_mode(mode))
+        torch.cuda.synchronize()
         fn, fl = cases[n]
         for _ in range(3):
             fn()
@@ -61,4 +72,5 @@ if __name__ == "__main__":
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         ts.sort()
-        print(f"{n:6s} {ts[3] * 1e3:8.1f} us  {fl / ts[3] / 1e9:7.1f} TF/s", flush=True)
+        print(f"{n:6s} mode {mode:2d} {ts[3] * 1e3:8.1f} us  {fl / ts[3] / 1e9:7.1f} TF/s", flush=True)
+    _lib.check(lib.tc_debug_set_gemm_mode(0))

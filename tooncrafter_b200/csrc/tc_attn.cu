@@ -647,6 +647,7 @@ __global__ void softmax_rows_kernel(__half* __restrict__ s, long long lds, int r
 using namespace tc_host;
 
 int tc_attention_v3(const TcAttention* d, int poly_of_8, cudaStream_t stream);   // tc_attn3.cu
+int tc_attention_xs(const TcAttention* d, cudaStream_t stream);                    // tc_attn3.cu (small K/V, 1-2 segments)
 
 // TC_ATTN_IMPL=v2 keeps single-segment problems on the second-generation kernel below (A/B runs);
 // TC_ATTN_POLY=n (0..4) sets how many of every 8 exponential pairs the v3 kernel evaluates on the FMA pipe.
@@ -669,6 +670,16 @@ extern "C" int tc_attention(const TcAttention* d, void* stream_v) {
         TC_CHECK_ARG(d->k[0] && d->v[0] && d->Lk[0] > 0 && d->kv_div[0] > 0, "tc_attention: bad kv segment");
         TC_CHECK_ARG(d->ldk[0] % 8 == 0 && d->ldv[0] % 8 == 0, "tc_attention: kv strides must be multiples of 8");
         return tc_attention_v3(d, attn_poly(), stream);
+    }
+    if (attn_impl_v3()) {
+        // short K/V (the 77 text + 16 image tokens of the cross attentions): resident-K/V kernel when the shape fits
+        bool ok = true;
+        for (int s = 0; s < d->n_seg; ++s)
+            ok = ok && d->k[s] && d->v[s] && d->Lk[s] > 0 && d->kv_div[s] > 0 && d->ldk[s] % 8 == 0 && d->ldv[s] % 8 == 0;
+        if (ok) {
+            const int rc = tc_attention_xs(d, stream);
+            if (rc != TC_ERR_INVALID) return rc;
+        }
     }
     AttnKParams p;
     memset(&p, 0, sizeof(p));

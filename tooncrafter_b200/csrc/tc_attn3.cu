@@ -135,9 +135,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_cons
         tc::mbar_init(bar_q, 1);
         for (int i = 0; i < kStages; ++i) {
             tc::mbar_init(&k_full[i], 1);
-            tc::mbar_init(&k_free[i], (uint32_t)ntiles);   // one tcgen05.commit per query tile releases a ring slot
+            tc::mbar_init(&k_free[i], 1);
             tc::mbar_init(&v_full[i], 1);
-            tc::mbar_init(&v_free[i], (uint32_t)ntiles);
+            tc::mbar_init(&v_free[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&s_full[i], 1);
@@ -207,67 +207,47 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_cons
         tc::tc_fence_after();
         if (tc::elect_one()) {
             const int nk = block_nk(0);
-            for (int w = 0; w < ntiles; ++w) {
-                issue_s(w, 0, nk);
-                tc::umma_commit(&k_free[0]);          // one arrival per query tile (the barrier counts ntiles)
-            }
+            for (int w = 0; w < ntiles; ++w) issue_s(w, 0, nk);
+            tc::umma_commit(&k_free[0]);
         }
         __syncwarp();
-        // Event-driven issue: the two query tiles are independent state machines
-        //     [S_w(g+1) once the softmax warps hold S_w(g) in registers]  ->  [O_w += P_w(g) V(g) once P_w(g) is in TMEM]
-        // polled round-robin with non-blocking barrier tests.  Issuing in a fixed order (tile 0 then tile 1) locks the two
-        // softmax warpgroups into the same phase — both in their MUFU-bound exponentials, then both idle on the XU while
-        // they wait for each other's MMAs (measured: 2836 cycles per key block instead of the 2048 the MUFU allows).
-        int gw[2] = {0, ntiles > 1 ? 0 : G};     // block whose PV is next, per tile
-        bool need_s[2] = {true, true};           // state: next action of the tile is S(g + 1)
-        const long long t_start = clock64();
-        while (gw[0] < G || gw[1] < G) {
-            if (clock64() - t_start > 20000000000LL) {   // ~10 s: a protocol bug traps instead of hanging the GPU
-                if (tc::elect_one()) printf("tc_attn3: MMA issuer timeout (block %d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z);
-                __trap();
-            }
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {
-                const int g = gw[w];
-                if (g >= G) continue;
-                if (need_s[w]) {
-                    if (g + 1 >= G) {
-                        need_s[w] = false;
-                    } else {
-                        const int st1 = (g + 1) % kStages;
-                        const uint32_t ph1 = (uint32_t)(((g + 1) / kStages) & 1);
-                        if (tc::mbar_try_wait(&s_free[w], (uint32_t)(g & 1)) && tc::mbar_try_wait(&k_full[st1], ph1)) {
-                            tc::tc_fence_after();
-                            if (tc::elect_one()) {
-                                issue_s(w, st1, block_nk(g + 1));
-                                tc::umma_commit(&k_free[st1]);
-                            }
-                            __syncwarp();
-                            need_s[w] = false;
-                        }
+        int st = 0;
+        uint32_t ph = 0;
+        for (int g = 0; g < G; ++g) {
+            const int nk = block_nk(g);
+            // ---- S of the NEXT block as soon as the softmax warps have pulled this block's S into registers
+            if (g + 1 < G) {
+                const int st1 = (st + 1 == kStages) ? 0 : st + 1;
+                const uint32_t ph1 = (st + 1 == kStages) ? (ph ^ 1u) : ph;
+                const int nk1 = block_nk(g + 1);
+                tc::mbar_wait(&k_full[st1], ph1);
+                for (int w = 0; w < ntiles; ++w) {
+                    tc::mbar_wait(&s_free[w], (uint32_t)(g & 1));
+                    tc::tc_fence_after();
+                    if (tc::elect_one()) {
+                        issue_s(w, st1, nk1);
+                        if (w == ntiles - 1) tc::umma_commit(&k_free[st1]);
                     }
-                } else {
-                    const int st = g % kStages;
-                    const uint32_t ph = (uint32_t)((g / kStages) & 1);
-                    if (tc::mbar_try_wait(&p_ready[w], (uint32_t)(g & 1)) && tc::mbar_try_wait(&v_full[st], ph)) {
-                        tc::tc_fence_after();
-                        if (tc::elect_one()) {
-                            const int nk = block_nk(g);
-                            const uint32_t idesc_o = tc::umma_idesc_f16(128, 64, 0, 1);   // B (= V tile [keys][64]) MN-major
-                            const uint64_t vd = tc::umma_desc_sw128(sV_a + (uint32_t)st * kTileBytes);
-                            for (int t = 0; t < nk / 16; ++t)
-                                tc::umma_f16_ts(tmem_base + kTmemO + (uint32_t)w * 64,
-                                                tmem_base + kTmemP + (uint32_t)w * 64 + (uint32_t)(t * 8), vd + (uint64_t)(t * 128),
-                                                idesc_o, (g != 0 || t != 0) ? 1u : 0u);
-                            tc::umma_commit(&o_full[w]);
-                            tc::umma_commit(&v_free[st]);
-                        }
-                        __syncwarp();
-                        gw[w] = g + 1;
-                        need_s[w] = true;
-                    }
+                    __syncwarp();
                 }
             }
+            // ---- O_w += P_w V for this block (P from tensor memory)
+            tc::mbar_wait(&v_full[st], ph);
+            for (int w = 0; w < ntiles; ++w) {
+                tc::mbar_wait(&p_ready[w], (uint32_t)(g & 1));
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                    const uint32_t idesc_o = tc::umma_idesc_f16(128, 64, 0, 1);   // B (= V tile [keys][64]) MN-major
+                    const uint64_t vd = tc::umma_desc_sw128(sV_a + (uint32_t)st * kTileBytes);
+                    for (int t = 0; t < nk / 16; ++t)
+                        tc::umma_f16_ts(tmem_base + kTmemO + (uint32_t)w * 64, tmem_base + kTmemP + (uint32_t)w * 64 + (uint32_t)(t * 8),
+                                        vd + (uint64_t)(t * 128), idesc_o, (g != 0 || t != 0) ? 1u : 0u);
+                    tc::umma_commit(&o_full[w]);
+                    if (w == ntiles - 1) tc::umma_commit(&v_free[st]);
+                }
+                __syncwarp();
+            }
+            if (++st == kStages) { st = 0; ph ^= 1u; }
         }
     } else if ((warp >> 2) < ntiles) {
         // ------------------------------------------------------------------------------ softmax warpgroups
@@ -311,8 +291,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_cons
             // ---- lazy rescale: keep the old reference maximum unless the row maximum grew by more than 2^8
             const bool grow = (m_new - m_run) * c > kRescaleThreshold;    // first block: (x - -inf) = +inf -> true
             const float m_use = grow ? m_new : m_run;
-            const float alpha = ex2((m_run - m_use) * c);                  // 1 for the rows that keep their maximum
-            const bool any_grow = g > 0 && __any_sync(0xffffffffu, grow);
+            if (g > 0) {
+                tc::mbar_wait(&o_full[w], (uint32_t)((g - 1) & 1));       // PV of the previous block retired: P and O are ours
+                tc::tc_fence_after();
+                if (__any_sync(0xffffffffu, grow)) {
+                    const float alpha = ex2((m_run - m_use) * c);          // 1 for the rows that keep their maximum
+                    l_run *= alpha;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        uint32_t r[16];
+                        tc::tmem_ld16(tmem_o + (uint32_t)(cc * 16), r);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                        tc::tmem_st16(tmem_o + (uint32_t)(cc * 16), r);
+                    }
+                    tc::tmem_st_wait();
+                }
+            }
             m_run = m_use;
             const float nm = -m_use * c;
             const u64 nm2 = pack2(nm, nm);
@@ -334,25 +330,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_cons
                 if (j & 1) sum_b = add2(sum_b, pack2(e0, e1));
                 else sum_a = add2(sum_a, pack2(e0, e1));
                 pk[j] = pack_h2(e0, e1);
-            }
-            // Only now must the previous block's PV MMA have retired (it reads P and accumulates into O): waiting here,
-            // after the ~1000-cycle exponential phase, instead of before it took a 5 % long-scoreboard stall off the
-            // critical path (profiles/r02_ncu_attn3_2560_first.txt).
-            if (g > 0) {
-                tc::mbar_wait(&o_full[w], (uint32_t)((g - 1) & 1));
-                tc::tc_fence_after();
-                if (any_grow) {
-                    l_run *= alpha;
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        uint32_t r[16];
-                        tc::tmem_ld16(tmem_o + (uint32_t)(cc * 16), r);
-                        tc::tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                        tc::tmem_st16(tmem_o + (uint32_t)(cc * 16), r);
-                    }
-                }
             }
             tc::tmem_st32(tmem_p, &pk[0]);
             tc::tmem_st32(tmem_p + 32, &pk[32]);
@@ -411,6 +388,210 @@ int launch_attn3(const Attn3Params& p, dim3 grid, size_t smem_bytes, cudaStream_
     return 0;
 }
 
+
+// ===================================================================================== small-KV cross attention
+// Text + image cross attention of the spatial transformers (lvdm/modules/attention.py:126-142 / 196-207): every query
+// attends to 77 text keys and to 16 image keys and the two softmax-weighted sums are ADDED.  93 keys is 2-3 % of a
+// self-attention's work per query tile: on the tcgen05 kernels (128-row tiles, TMEM, mbarrier pipelines) the launch
+// is pure latency — 50-85 TF/s, and a persistent tcgen05 variant with resident K/V measured no better (only two
+// query tiles fit in TMEM at a time).  This kernel takes the other road: warp-level mma.sync with MANY warps in
+// flight.  A CTA (4 warps) keeps the K / V rows of both segments of one (frame, head) in shared memory and every warp
+// streams 16-query groups:  S = Q K^T (m16n8k16, K fragments by ldmatrix) -> two independent fp32 softmaxes on the
+// accumulator fragments, normalised BEFORE the fp16 rounding -> P = hi + lo fp16 parts (with 16 image keys the rounding
+// of P is not averaged away) -> O = P V (V fragments by ldmatrix.trans) -> fp16 -> global.
+// Needs ceil16(Lk0) + ceil16(Lk1) <= 96 keys (12 n-tiles of S accumulators per thread).
+constexpr int kXsMaxNT = 12;           // n-tiles (8 keys each) of S per warp
+constexpr int kXsThreads = 128;
+
+struct AttnXsParams {
+    const __half* q;
+    const __half* k[2];
+    const __half* v[2];
+    long long ldq, ldk[2], ldv[2];
+    int Lq, heads, n_seg, Lk[2], kv_div[2];
+    __half* out;
+    long long ldo;
+    float scale_log2;
+};
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kXsThreads, 3) tc_attn_xs_kernel(const AttnXsParams p) {
+    tc::pdl_wait();   // no early launch_dependents (see temporal_attn_mma_kernel)
+    __shared__ __align__(128) uint8_t sK[kXsMaxNT * 8 * 128];   // [key][64 halfs], 16-byte chunks XOR-swizzled by key & 7
+    __shared__ __align__(128) uint8_t sV[kXsMaxNT * 8 * 128];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int head = blockIdx.y, qb = blockIdx.z;
+    const int nk0 = (p.Lk[0] + 15) & ~15, nk1 = p.n_seg > 1 ? ((p.Lk[1] + 15) & ~15) : 0;
+    const int ntot = (nk0 + nk1) >> 3, nt0 = nk0 >> 3;
+
+    // ---- K / V of both segments -> shared memory (rows past a segment's length are zero)
+    for (int ch = tid; ch < (nk0 + nk1) * 8; ch += kXsThreads) {
+        const int row = ch >> 3, c16 = ch & 7;
+        const int sgm = row >= nk0 ? 1 : 0;
+        const int r = row - (sgm ? nk0 : 0);
+        uint4 uk = make_uint4(0u, 0u, 0u, 0u), uv = uk;
+        if (r < p.Lk[sgm]) {
+            const long long kvb = qb / p.kv_div[sgm];
+            uk = *reinterpret_cast<const uint4*>(p.k[sgm] + (kvb * p.Lk[sgm] + r) * p.ldk[sgm] + head * 64 + c16 * 8);
+            uv = *reinterpret_cast<const uint4*>(p.v[sgm] + (kvb * p.Lk[sgm] + r) * p.ldv[sgm] + head * 64 + c16 * 8);
+        }
+        const int off = row * 128 + ((c16 ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(sK + off) = uk;
+        *reinterpret_cast<uint4*>(sV + off) = uv;
+    }
+    __syncthreads();
+    const uint32_t sK_a = tc::smem_u32(sK), sV_a = tc::smem_u32(sV);
+    const float c = p.scale_log2;
+    const int n_groups = (p.Lq + 15) >> 4;
+
+    for (int grp = (int)blockIdx.x * 4 + warp; grp < n_groups; grp += (int)gridDim.x * 4) {
+        const int r0 = grp * 16 + g8, r1 = r0 + 8;
+        const bool ok0 = r0 < p.Lq, ok1 = r1 < p.Lq;
+        const __half* q0p = p.q + ((long long)qb * p.Lq + r0) * p.ldq + head * 64;
+        const __half* q1p = p.q + ((long long)qb * p.Lq + r1) * p.ldq + head * 64;
+        uint32_t qa[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const int col = 16 * ks + 2 * t4;
+            qa[ks][0] = ok0 ? *reinterpret_cast<const uint32_t*>(q0p + col) : 0u;
+            qa[ks][1] = ok1 ? *reinterpret_cast<const uint32_t*>(q1p + col) : 0u;
+            qa[ks][2] = ok0 ? *reinterpret_cast<const uint32_t*>(q0p + col + 8) : 0u;
+            qa[ks][3] = ok1 ? *reinterpret_cast<const uint32_t*>(q1p + col + 8) : 0u;
+        }
+        // ---- S = Q K^T: per n-tile two ldmatrix.x4 (d chunks 0-31, 32-63 of keys 8nt..8nt+7)
+        float sacc[kXsMaxNT][4];
+#pragma unroll
+        for (int nt = 0; nt < kXsMaxNT; ++nt) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sacc[nt][i] = 0.f;
+            if (nt < ntot) {
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    // lane i supplies the row address of matrix i / 8: matrices = 16-byte d-chunks 4hf .. 4hf+3 of these keys
+                    const int krow = 8 * nt + (lane & 7);
+                    const int chunk = 4 * hf + (lane >> 3);
+                    const uint32_t addr = sK_a + (uint32_t)(krow * 128 + ((chunk ^ (krow & 7)) << 4));
+                    uint32_t b0, b1, b2, b3;
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                                 : "r"(addr));
+                    mma16816(sacc[nt], qa[2 * hf], b0, b1);
+                    mma16816(sacc[nt], qa[2 * hf + 1], b2, b3);
+                }
+            }
+        }
+        // ---- two independent softmaxes: keys [0, Lk0) and [nk0, nk0 + Lk1); rows g8 (values 0,1) and g8 + 8 (values 2,3)
+        float m00 = -INFINITY, m01 = -INFINITY, m10 = -INFINITY, m11 = -INFINITY;   // m<seg><row half>
+#pragma unroll
+        for (int nt = 0; nt < kXsMaxNT; ++nt) {
+            if (nt < ntot) {
+                const bool s1 = nt >= nt0;
+                const int key0 = 8 * nt + 2 * t4 - (s1 ? nk0 : 0);
+                const int lim = s1 ? p.Lk[1] : p.Lk[0];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const bool okk = key0 + i < lim;
+                    sacc[nt][i] = okk ? sacc[nt][i] : -INFINITY;
+                    sacc[nt][2 + i] = okk ? sacc[nt][2 + i] : -INFINITY;
+                    if (s1) { m10 = fmaxf(m10, sacc[nt][i]); m11 = fmaxf(m11, sacc[nt][2 + i]); }
+                    else { m00 = fmaxf(m00, sacc[nt][i]); m01 = fmaxf(m01, sacc[nt][2 + i]); }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            m00 = fmaxf(m00, __shfl_xor_sync(0xffffffffu, m00, o));
+            m01 = fmaxf(m01, __shfl_xor_sync(0xffffffffu, m01, o));
+            m10 = fmaxf(m10, __shfl_xor_sync(0xffffffffu, m10, o));
+            m11 = fmaxf(m11, __shfl_xor_sync(0xffffffffu, m11, o));
+        }
+        const float n00 = -m00 * c, n01 = -m01 * c;
+        const float n10 = (m10 == -INFINITY) ? 0.f : -m10 * c, n11 = (m11 == -INFINITY) ? 0.f : -m11 * c;
+        float l00 = 0.f, l01 = 0.f, l10 = 0.f, l11 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < kXsMaxNT; ++nt) {
+            if (nt < ntot) {
+                const bool s1 = nt >= nt0;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float e0 = ex2(fmaf(sacc[nt][i], c, s1 ? n10 : n00));
+                    const float e1 = ex2(fmaf(sacc[nt][2 + i], c, s1 ? n11 : n01));
+                    sacc[nt][i] = e0;
+                    sacc[nt][2 + i] = e1;
+                    if (s1) { l10 += e0; l11 += e1; } else { l00 += e0; l01 += e1; }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            l00 += __shfl_xor_sync(0xffffffffu, l00, o);
+            l01 += __shfl_xor_sync(0xffffffffu, l01, o);
+            l10 += __shfl_xor_sync(0xffffffffu, l10, o);
+            l11 += __shfl_xor_sync(0xffffffffu, l11, o);
+        }
+        const float i00 = 1.0f / l00, i01 = 1.0f / l01;
+        const float i10 = l10 > 0.f ? 1.0f / l10 : 0.f, i11 = l11 > 0.f ? 1.0f / l11 : 0.f;
+        // ---- O = P V with P = hi + lo (fp16 parts of the normalised probabilities)
+        float oacc[8][4];
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) oacc[nd][i] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < kXsMaxNT / 2; ++kk) {
+            if (2 * kk < ntot) {
+                const bool s1 = 2 * kk >= nt0;          // nk0 is a multiple of 16: a k-step never straddles the segments
+                const float ia = s1 ? i10 : i00, ib = s1 ? i11 : i01;
+                uint32_t ph[4], pl[4];
+                {
+                    const float a0 = sacc[2 * kk][0] * ia, a1 = sacc[2 * kk][1] * ia, b0 = sacc[2 * kk][2] * ib, b1 = sacc[2 * kk][3] * ib;
+                    const float c0 = sacc[2 * kk + 1][0] * ia, c1 = sacc[2 * kk + 1][1] * ia, d0 = sacc[2 * kk + 1][2] * ib, d1 = sacc[2 * kk + 1][3] * ib;
+                    const __half2 h0 = __floats2half2_rn(a0, a1), h1 = __floats2half2_rn(b0, b1);
+                    const __half2 h2 = __floats2half2_rn(c0, c1), h3 = __floats2half2_rn(d0, d1);
+                    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+                    ph[0] = *reinterpret_cast<const uint32_t*>(&h0);
+                    ph[1] = *reinterpret_cast<const uint32_t*>(&h1);
+                    ph[2] = *reinterpret_cast<const uint32_t*>(&h2);
+                    ph[3] = *reinterpret_cast<const uint32_t*>(&h3);
+                    pl[0] = pack_h2(a0 - f0.x, a1 - f0.y);
+                    pl[1] = pack_h2(b0 - f1.x, b1 - f1.y);
+                    pl[2] = pack_h2(c0 - f2.x, c1 - f2.y);
+                    pl[3] = pack_h2(d0 - f3.x, d1 - f3.y);
+                }
+#pragma unroll
+                for (int nd = 0; nd < 8; nd += 2) {
+                    // matrices (keys 16kk..+7, d-chunk nd), (keys 16kk+8..+15, nd), (keys ..+7, nd+1), (keys +8.., nd+1)
+                    const int vrow = 16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8;
+                    const int chunk = nd + (lane >> 4);
+                    const uint32_t addr = sV_a + (uint32_t)(vrow * 128 + ((chunk ^ (vrow & 7)) << 4));
+                    uint32_t b0, b1, b2, b3;
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                                 : "r"(addr));
+                    mma16816(oacc[nd], pl, b0, b1);
+                    mma16816(oacc[nd + 1], pl, b2, b3);
+                    mma16816(oacc[nd], ph, b0, b1);
+                    mma16816(oacc[nd + 1], ph, b2, b3);
+                }
+            }
+        }
+        __half* o0p = p.out + ((long long)qb * p.Lq + r0) * p.ldo + head * 64;
+        __half* o1p = p.out + ((long long)qb * p.Lq + r1) * p.ldo + head * 64;
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd) {
+            if (ok0) *reinterpret_cast<uint32_t*>(o0p + 8 * nd + 2 * t4) = pack_h2(oacc[nd][0], oacc[nd][1]);
+            if (ok1) *reinterpret_cast<uint32_t*>(o1p + 8 * nd + 2 * t4) = pack_h2(oacc[nd][2], oacc[nd][3]);
+        }
+    }
+}
+
 }  // namespace
 
 using namespace tc_host;
@@ -458,5 +639,43 @@ int tc_attention_v3(const TcAttention* d, int poly_of_8, cudaStream_t stream) {
     if (rc) return rc;
     count_launch();
     TC_CHECK_LAUNCH("tc_attn3_kernel");
+    return TC_OK;
+}
+
+// Cross attention over one or two short K/V segments (text + image tokens) through the resident-K/V mma.sync kernel.
+// Returns TC_ERR_INVALID (without setting an error) when the shape does not fit: the caller falls back.
+int tc_attention_xs(const TcAttention* d, cudaStream_t stream) {
+    const int nk0 = (d->Lk[0] + 15) & ~15, nk1 = d->n_seg > 1 ? ((d->Lk[1] + 15) & ~15) : 0;
+    if (nk0 + nk1 > 8 * kXsMaxNT) return TC_ERR_INVALID;
+    if ((d->ldq % 8) || (d->ldo % 2)) return TC_ERR_INVALID;
+    AttnXsParams p;
+    memset(&p, 0, sizeof(p));
+    p.q = reinterpret_cast<const __half*>(d->q);
+    p.ldq = d->ldq;
+    for (int s = 0; s < d->n_seg; ++s) {
+        p.k[s] = reinterpret_cast<const __half*>(d->k[s]);
+        p.v[s] = reinterpret_cast<const __half*>(d->v[s]);
+        p.ldk[s] = d->ldk[s];
+        p.ldv[s] = d->ldv[s];
+        p.Lk[s] = d->Lk[s];
+        p.kv_div[s] = d->kv_div[s];
+    }
+    p.Lq = d->Lq;
+    p.heads = d->heads;
+    p.n_seg = d->n_seg;
+    p.out = reinterpret_cast<__half*>(d->out);
+    p.ldo = d->ldo;
+    p.scale_log2 = d->scale * 1.4426950408889634f;
+    // ~4 waves of CTAs (3 resident per SM); each CTA streams its share of the 16-query groups of one (frame, head)
+    const long long pairs = (long long)d->heads * d->q_batches;
+    const int n_groups = (d->Lq + 15) / 16;
+    long long split = (12LL * sm_count() + pairs - 1) / pairs;
+    const long long max_split = (n_groups + 3) / 4;
+    if (split > max_split) split = max_split;
+    if (split < 1) split = 1;
+    dim3 grid((unsigned)split, d->heads, d->q_batches);
+    tc_host::launch(tc_attn_xs_kernel, grid, dim3(kXsThreads), 0, stream, 1, p);
+    count_launch();
+    TC_CHECK_LAUNCH("tc_attn_xs_kernel");
     return TC_OK;
 }

@@ -38,6 +38,25 @@ constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM column offset of the second accumulator
 
+// Division by a launch constant as multiply-high + shift (exact for dividends below 2^31): the per-tile coordinate
+// decode used ~10 generic integer divisions, 1000-2400 cycles of dependent latency per tile on the epilogue warps of
+// the short-K launches (in-kernel timeline, profiles/r02_gemm_epilogue_timeline.txt).
+struct FastDiv {
+    uint32_t d, mul, shr;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f{d ? d : 1u, 0u, 0u};
+    uint32_t lg = 0;
+    while ((2u << lg) <= f.d && lg < 31) ++lg;                 // floor(log2 d)
+    f.shr = lg;
+    if ((f.d & (f.d - 1)) != 0)                                // not a power of two
+        f.mul = (uint32_t)((((unsigned long long)1 << (32 + lg)) + f.d - 1) / f.d);
+    return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+    return (int)(f.mul ? (__umulhi((uint32_t)n, f.mul) >> f.shr) : ((uint32_t)n >> f.shr));
+}
+
 struct alignas(64) GemmKParams {
     CUtensorMap tmA;
     CUtensorMap tmB;
@@ -61,6 +80,7 @@ struct alignas(64) GemmKParams {
     int tiles_m, tiles_nn;          // tiles along M and along N
     int BN;
     int raster;                     // tile order, see TC_DECODE_TILE
+    FastDiv fd_nn, fd_mu, fd_x, fd_y, fd_xy, fd_b2;   // tiles_nn, M-tile units, tiles_x, tiles_y, tiles_x*tiles_y, bias2_rows_per
     int stage_bufs;                 // 1 or 2 output staging boxes (2: short-K launches, whose epilogue is the bottleneck)
     int n_cols;
     int stages;
@@ -220,14 +240,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     // so A comes from DRAM once and from L2 for the other N tiles (the N-major order streamed the 100-200 MB A operand
     // of the FF2 GEMMs once per N tile: 2-3.3x DRAM traffic, profiles/r01_unet_b2_launches_final.txt).  The host makes
     // the number of work units a multiple of tiles_nn when the weights are resident, so a CTA's N tile never changes.
-#define TC_TILE_NT(tile) (p.raster ? (tile) % p.tiles_nn : (tile) / tiles_mu)
+#define TC_TILE_NT(tile) (p.raster ? (tile) - fdiv((tile), p.fd_nn) * p.tiles_nn : fdiv((tile), p.fd_mu))
 #define TC_DECODE_TILE(tile)                                                   \
     const int nt = TC_TILE_NT(tile);                                           \
-    const int mtu_ = p.raster ? (tile) / p.tiles_nn : (tile) - nt * tiles_mu;  \
+    const int mtu_ = p.raster ? fdiv((tile), p.fd_nn) : (tile) - nt * tiles_mu;  \
     const int mt = mtu_ * (kPair ? 2 : 1) + (int)rank;                         \
-    const int tx = mt % p.tiles_x;                                             \
-    const int ty = (mt / p.tiles_x) % p.tiles_y;                               \
-    const int tn = mt / (p.tiles_x * p.tiles_y);
+    const int mtx_ = fdiv(mt, p.fd_x);                                         \
+    const int tx = mt - mtx_ * p.tiles_x;                                      \
+    const int tn = fdiv(mt, p.fd_xy);                                          \
+    const int ty = mtx_ - tn * p.tiles_y;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -417,6 +438,34 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         int acc = 0;
         uint32_t acc_phase = 0;
         int ti = 0;
+        // {mean, rstd} of output row m for the LayerNorm folded into this GEMM (1, 0 without one)
+        auto ln_row_stats = [&](bool ok, long long mrow, float& mean, float& rstd) {
+            mean = 0.f;
+            rstd = 1.f;
+            if (!p.ln_stats || !ok) return;
+            if (p.ln_nslots > 0) {
+                // partial {sum, sumsq} slots written by the producer GEMM's epilogue (fixed order: deterministic)
+                float s1 = 0.f, s2 = 0.f;
+                const float2* ps = p.ln_stats + mrow * p.ln_nslots;
+#pragma unroll 4
+                for (int i = 0; i < p.ln_nslots; ++i) {
+                    const float2 st = __ldg(ps + i);
+                    s1 += st.x;
+                    s2 += st.y;
+                }
+                mean = s1 * p.ln_inv_c;
+                const float var = fmaxf(s2 * p.ln_inv_c - mean * mean, 0.f);
+                rstd = rsqrtf(var + p.ln_eps);
+            } else {
+                const float2 st = __ldg(p.ln_stats + mrow);
+                mean = st.x;
+                rstd = st.y;
+            }
+        };
+        float ln_mean = 0.f, ln_rstd = 1.f;
+        float2 pre[4];                                     // next tile's partial slots (ln_nslots <= 4), raw
+        const bool pre_ok = p.ln_stats != nullptr && p.ln_nslots >= 1 && p.ln_nslots <= 4;
+        bool pre_row_ok = false;
         for (int tile = unit; tile < total_tiles; tile += n_units, ++ti) {
             TC_DECODE_TILE(tile)
             const int x = tx * p.TW + rx, y = ty * p.TH + ry, n = tn * p.TN + rn;
@@ -424,26 +473,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             const long long m = ((long long)n * p.oH + y) * p.oW + x;
             const __half* rrow = (p.res && p.res_kblocks == 0 && row_ok) ? p.res + m * p.ldr + (long long)nt * BN : nullptr;
 
-            float ln_mean = 0.f, ln_rstd = 1.f;
-            if (p.ln_stats && row_ok) {
-                if (p.ln_nslots > 0) {
-                    // partial {sum, sumsq} slots written by the producer GEMM's epilogue (fixed order: deterministic)
-                    float s1 = 0.f, s2 = 0.f;
-                    const float2* ps = p.ln_stats + m * p.ln_nslots;
-#pragma unroll 4
-                    for (int i = 0; i < p.ln_nslots; ++i) {
-                        const float2 st = __ldg(ps + i);
-                        s1 += st.x;
-                        s2 += st.y;
-                    }
-                    ln_mean = s1 * p.ln_inv_c;
-                    const float var = fmaxf(s2 * p.ln_inv_c - ln_mean * ln_mean, 0.f);
-                    ln_rstd = rsqrtf(var + p.ln_eps);
-                } else {
-                    const float2 st = __ldg(p.ln_stats + m);
-                    ln_mean = st.x;
-                    ln_rstd = st.y;
-                }
+            // folded-LayerNorm row statistics: loaded one tile ahead (below, after the accumulator wait), so their L2 round
+            // trip hides behind this tile's epilogue instead of heading the next one (4.6 % of the samples of the GEGLU
+            // launch sat on the first use of these loads)
+            if (ti == 0 || !pre_ok) {
+                ln_row_stats(row_ok, m, ln_mean, ln_rstd);
+            } else {
+                // finish the partials fetched during the previous tile (only now are the loaded values touched)
+                const float s1 = (pre[0].x + pre[1].x) + (pre[2].x + pre[3].x), s2 = (pre[0].y + pre[1].y) + (pre[2].y + pre[3].y);
+                ln_mean = s1 * p.ln_inv_c;
+                ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
+                if (!pre_row_ok) { ln_mean = 0.f; ln_rstd = 1.f; }
             }
             const float ln_rm = -ln_rstd * ln_mean;
             // ---- residual prefetch (up to 128 columns = 16 x 16 B per thread)
@@ -467,17 +507,34 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 const int e = (int)threadIdx.x - 64;            // 0..255 over the 8 epilogue warps
                 const int col = nt * BN + e;
                 const bool ok = e < BN && col < p.n_cols;
-                if (p.bias) wb[e] = ok ? __ldg(p.bias + col) : 0.f;
-                if (p.ln_u) wb[256 + e] = ok ? __ldg(p.ln_u + col) : 0.f;
+                // both vectors are always defined (zeros when the launch has no bias / no folded LayerNorm): the TMA-store
+                // epilogues then run ONE branch-free form,  rstd * acc + (rm * u + bias)  with rstd = 1, rm = 0 by default
+                wb[e] = (ok && p.bias) ? __ldg(p.bias + col) : 0.f;
+                wb[256 + e] = (ok && p.ln_u) ? __ldg(p.ln_u + col) : 0.f;
             }
             float* sbias = s_epi + sb * 512;
             float* su = sbias + 256;
+            const uint32_t sbias_a = tc::smem_u32(sbias);          // u lives 1024 bytes (256 floats) behind the bias
 
             if (threadIdx.x == 64) { TC_TRACE(5, ti) }
             tc::mbar_wait(&tfull_bar[acc], acc_phase);
             tc::tc_fence_after();
             if (threadIdx.x == 64) { TC_TRACE(6, ti) }
             if (restage) asm volatile("bar.sync 1, 256;" ::: "memory");       // staging visible to all epilogue warps
+            if (pre_ok && tile + n_units < total_tiles) {
+                const int tile2 = tile + n_units;
+                const int nt2 = TC_TILE_NT(tile2);
+                const int mtu2 = p.raster ? fdiv(tile2, p.fd_nn) : tile2 - nt2 * tiles_mu;
+                const int mt2 = mtu2 * (kPair ? 2 : 1) + (int)rank;
+                const int mtx2 = fdiv(mt2, p.fd_x), tn2 = fdiv(mt2, p.fd_xy);
+                const int x2 = (mt2 - mtx2 * p.tiles_x) * p.TW + rx, y2 = (mtx2 - tn2 * p.tiles_y) * p.TH + ry;
+                const int n2 = tn2 * p.TN + rn;
+                pre_row_ok = (rn < p.TN) && (x2 < p.oW) && (y2 < p.oH) && (n2 < p.oN);
+                const float2* ps = p.ln_stats + (((long long)n2 * p.oH + y2) * p.oW + x2) * p.ln_nslots;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    pre[i] = (pre_row_ok && i < p.ln_nslots) ? __ldg(ps + i) : make_float2(0.f, 0.f);
+            }
             if (threadIdx.x == 64) { TC_TRACE(15, ti) }
             const uint32_t taddr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(q * 32) << 16);
 
@@ -492,12 +549,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 // (the in-kernel timeline showed ~1400 cycles per chunk, mostly that wait).
                 const int half_bn = BN >> 1;
                 const __half* b2row =
-                    p.bias2 ? p.bias2 + (row_ok ? (m / p.bias2_rows_per) : 0) * p.bias2_ld + (long long)nt * BN : nullptr;
+                    p.bias2 ? p.bias2 + (long long)(row_ok ? fdiv((int)m, p.fd_b2) : 0) * p.bias2_ld + (long long)nt * BN : nullptr;
                 const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
                 const int dbg = g_tc_gemm_debug;
                 const tc::f32x2 rstd2 = tc::pk2(ln_rstd, ln_rstd), rm2 = tc::pk2(ln_rm, ln_rm);
                 const tc::f32x2 scale2 = tc::pk2(p.acc_scale, p.acc_scale);
                 uint32_t r[32];
+                uint32_t gr[4][16];                                    // GEGLU: {value, gate} x two 16-column halves of a chunk
                 tc::f32x2 rs_sum2 = 0ull, rs_sq2 = 0ull;
                 if (kEpi == 0 && cg * 32 < width) tc::tmem_ld32(taddr + (uint32_t)(cg * 32), r);
 #pragma unroll 1
@@ -505,6 +563,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     const int c = (cg + 2 * jc) * 32;
                     if (c >= width) break;
                     uint32_t pk[16];                                   // the chunk's 32 outputs of this row, fp16 pairs
+                    if (threadIdx.x == 64 && jc == 0) { TC_TRACE(8, ti) }
                     if constexpr (kEpi == 0) {
                         // register-path residual (scaled accumulators only; otherwise it rides the tensor core)
                         uint4 rr[4];
@@ -518,22 +577,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                         for (int i = 0; i < 16; ++i) v[i] = tc::pk2u(r[2 * i], r[2 * i + 1]);
                         // next chunk's accumulator read flies while this one is finished, staged and stored
                         if (c + 64 < width) tc::tmem_ld32(taddr + (uint32_t)(c + 64), r);
-                        if (p.ln_u) {
-                            // rstd*(acc - mean*u) + bias  ==  rstd*acc + (bias - rstd*mean*u): two packed FMAs per pair
+                        // rstd*(acc - mean*u) + bias  ==  rstd*acc + (rm*u + bias), rm = -rstd*mean: two packed FMAs per pair
+                        // (rstd = 1, rm = 0, u = 0 without a folded LayerNorm: exactly acc + bias).  The per-column vectors
+                        // are read with 32-bit shared addresses: through generic pointers every read cost six 64-bit
+                        // address instructions (profiles/r02_ncu_gemm_geglu_insitu.txt).
+                        {
+                            const uint32_t ab = sbias_a + (uint32_t)c * 4u, au = ab + 1024u;
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const float4 u4 = reinterpret_cast<const float4*>(su + c)[i];
-                                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (p.bias) b4 = reinterpret_cast<const float4*>(sbias + c)[i];
+                                float4 u4, b4;
+                                tc::lds128(au + 16u * i, u4);
+                                tc::lds128(ab + 16u * i, b4);
                                 v[2 * i] = tc::fma2(rstd2, v[2 * i], tc::fma2(rm2, tc::pk2(u4.x, u4.y), tc::pk2(b4.x, b4.y)));
                                 v[2 * i + 1] = tc::fma2(rstd2, v[2 * i + 1], tc::fma2(rm2, tc::pk2(u4.z, u4.w), tc::pk2(b4.z, b4.w)));
-                            }
-                        } else if (p.bias) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float4 b4 = reinterpret_cast<const float4*>(sbias + c)[i];
-                                v[2 * i] = tc::add2(v[2 * i], tc::pk2(b4.x, b4.y));
-                                v[2 * i + 1] = tc::add2(v[2 * i + 1], tc::pk2(b4.z, b4.w));
                             }
                         }
                         if (b2row) {
@@ -571,41 +627,51 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                             }
                         }
                     } else {
-                        // weight rows of this N tile are [value half (BN/2) | gate half (BN/2)]
+                        // weight rows of this N tile are [value half (BN/2) | gate half (BN/2)].  All four 16-column TMEM
+                        // reads of a chunk are in flight at once, and the NEXT chunk's reads are issued right after this
+                        // chunk's arithmetic, so their latency (~200 cycles each) hides behind the staging / TMA store.
+                        if (jc == 0) {
+                            tc::tmem_ld16(taddr + (uint32_t)c, gr[0]);
+                            tc::tmem_ld16(taddr + (uint32_t)(half_bn + c), gr[1]);
+                            tc::tmem_ld16(taddr + (uint32_t)(c + 16), gr[2]);
+                            tc::tmem_ld16(taddr + (uint32_t)(half_bn + c + 16), gr[3]);
+                        }
+                        tc::tmem_ld_wait();
+                        if (threadIdx.x == 64 && jc == 0) { TC_TRACE(14, ti) }   // TMEM reads landed
 #pragma unroll
                         for (int h16 = 0; h16 < 2; ++h16) {
-                            uint32_t ra[16], rg[16];
+                            const uint32_t (&ra)[16] = gr[2 * h16];
+                            const uint32_t (&rg)[16] = gr[2 * h16 + 1];
                             const int cc = c + h16 * 16;
-                            tc::tmem_ld16(taddr + (uint32_t)cc, ra);
-                            tc::tmem_ld16(taddr + (uint32_t)(half_bn + cc), rg);
-                            tc::tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
-                                if (p.bias) {
-                                    ba = reinterpret_cast<const float4*>(sbias + cc)[i];
-                                    bg = reinterpret_cast<const float4*>(sbias + half_bn + cc)[i];
-                                }
+                                const uint32_t aa = sbias_a + (uint32_t)cc * 4u + 16u * i, ag = aa + (uint32_t)half_bn * 4u;
+                                float4 ba, bg, ua, ug;
+                                tc::lds128(aa, ba);
+                                tc::lds128(ag, bg);
+                                tc::lds128(aa + 1024u, ua);
+                                tc::lds128(ag + 1024u, ug);
                                 tc::f32x2 a01 = tc::pk2u(ra[4 * i], ra[4 * i + 1]), a23 = tc::pk2u(ra[4 * i + 2], ra[4 * i + 3]);
                                 tc::f32x2 g01 = tc::pk2u(rg[4 * i], rg[4 * i + 1]), g23 = tc::pk2u(rg[4 * i + 2], rg[4 * i + 3]);
-                                if (p.ln_u) {
-                                    const float4 ua = reinterpret_cast<const float4*>(su + cc)[i];
-                                    const float4 ug = reinterpret_cast<const float4*>(su + half_bn + cc)[i];
-                                    a01 = tc::fma2(rstd2, a01, tc::fma2(rm2, tc::pk2(ua.x, ua.y), tc::pk2(ba.x, ba.y)));
-                                    a23 = tc::fma2(rstd2, a23, tc::fma2(rm2, tc::pk2(ua.z, ua.w), tc::pk2(ba.z, ba.w)));
-                                    g01 = tc::fma2(rstd2, g01, tc::fma2(rm2, tc::pk2(ug.x, ug.y), tc::pk2(bg.x, bg.y)));
-                                    g23 = tc::fma2(rstd2, g23, tc::fma2(rm2, tc::pk2(ug.z, ug.w), tc::pk2(bg.z, bg.w)));
-                                } else {
-                                    a01 = tc::add2(a01, tc::pk2(ba.x, ba.y));
-                                    a23 = tc::add2(a23, tc::pk2(ba.z, ba.w));
-                                    g01 = tc::add2(g01, tc::pk2(bg.x, bg.y));
-                                    g23 = tc::add2(g23, tc::pk2(bg.z, bg.w));
-                                }
+                                a01 = tc::fma2(rstd2, a01, tc::fma2(rm2, tc::pk2(ua.x, ua.y), tc::pk2(ba.x, ba.y)));
+                                a23 = tc::fma2(rstd2, a23, tc::fma2(rm2, tc::pk2(ua.z, ua.w), tc::pk2(ba.z, ba.w)));
+                                g01 = tc::fma2(rstd2, g01, tc::fma2(rm2, tc::pk2(ug.x, ug.y), tc::pk2(bg.x, bg.y)));
+                                g23 = tc::fma2(rstd2, g23, tc::fma2(rm2, tc::pk2(ug.z, ug.w), tc::pk2(bg.z, bg.w)));
                                 pk[h16 * 8 + 2 * i] = tc::h2_from_f2(tc::geglu_mul2(a01, g01));
                                 pk[h16 * 8 + 2 * i + 1] = tc::h2_from_f2(tc::geglu_mul2(a23, g23));
                             }
                         }
+                        {
+                            const int cn = c + 64;                       // this column group's next chunk
+                            if (cn < width) {
+                                tc::tmem_ld16(taddr + (uint32_t)cn, gr[0]);
+                                tc::tmem_ld16(taddr + (uint32_t)(half_bn + cn), gr[1]);
+                                tc::tmem_ld16(taddr + (uint32_t)(cn + 16), gr[2]);
+                                tc::tmem_ld16(taddr + (uint32_t)(half_bn + cn + 16), gr[3]);
+                            }
+                        }
                     }
+                    if (threadIdx.x == 64 && jc == 0) { TC_TRACE(9, ti) }      // math done
                     // two staging boxes in rotation: only the store issued two chunks ago must have drained this one
                     const uint32_t buf = n_stores & (uint32_t)(p.stage_bufs - 1);
                     uint8_t* stg_b = stg + buf * 16384u;
@@ -617,6 +683,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     if (warp_box) __syncwarp();
                     else if (cg == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
                     else asm volatile("bar.sync 3, 128;" ::: "memory");
+                    if (threadIdx.x == 64 && jc == 0) { TC_TRACE(10, ti) }     // staging box free
                     if (!(dbg & 16))
 #pragma unroll
                     for (int hh = 0; hh < 4; ++hh) {
@@ -626,9 +693,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                                      : "memory");
                     }
                     if (!(dbg & 8)) tc::fence_proxy_async_smem();
+                    if (threadIdx.x == 64 && jc == 0) { TC_TRACE(11, ti) }     // staged + fenced
                     if (warp_box) __syncwarp();
                     else if (cg == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
                     else asm volatile("bar.sync 3, 128;" ::: "memory");
+                    if (threadIdx.x == 64 && jc == 0) { TC_TRACE(12, ti) }
                     if (store_leader && !(dbg & 1)) {
                         if (warp_box) {
                             if (warp_rows_in_tile) {
@@ -640,6 +709,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                             tc::bulk_commit_group();
                         }
                     }
+                    if (threadIdx.x == 64 && jc == 0) { TC_TRACE(13, ti) }     // store issued
                 }
                 float rs_sum = 0.f, rs_sq = 0.f;
                 if (kEpi == 0 && p.row_stats) {
@@ -668,7 +738,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             } else if (!geglu) {
                 __half* orow = p.out + m * p.ldc + (long long)nt * BN;
                 const __half* b2row =
-                    p.bias2 ? p.bias2 + (row_ok ? (m / p.bias2_rows_per) : 0) * p.bias2_ld + (long long)nt * BN : nullptr;
+                    p.bias2 ? p.bias2 + (long long)(row_ok ? fdiv((int)m, p.fd_b2) : 0) * p.bias2_ld + (long long)nt * BN : nullptr;
                 const float* brow = p.bias ? p.bias + (long long)nt * BN : nullptr;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -944,6 +1014,7 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
     p.tiles_y = (d->oH + p.TH - 1) / p.TH;
     p.tiles_n = (d->oN + p.TN - 1) / p.TN;
     p.tiles_m = p.tiles_x * p.tiles_y * p.tiles_n;
+    TC_CHECK_ARG((long long)d->oN * d->oH * d->oW < (1LL << 31), "tc_conv_gemm: more than 2^31 output rows");
     static const char* pair_env = getenv("TC_GEMM_PAIR");       // "0" / "1" force (A/B testing), unset = heuristic
     TileChoice choice = choose_tiles(p.tiles_m, d->n_cols, d->taps * (d->a_C / kBlockK), BN, sm_count());
     BN = choice.bn;
@@ -1104,6 +1175,12 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
             }
         }
     }
+    p.fd_nn = make_fastdiv((uint32_t)p.tiles_nn);
+    p.fd_mu = make_fastdiv((uint32_t)(pair ? (p.tiles_m + 1) / 2 : p.tiles_m));
+    p.fd_x = make_fastdiv((uint32_t)p.tiles_x);
+    p.fd_y = make_fastdiv((uint32_t)p.tiles_y);
+    p.fd_xy = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y));
+    p.fd_b2 = make_fastdiv((uint32_t)p.bias2_rows_per);
     const int grid = pair ? 2 * units : units;
     launch(kernels[pair ? 1 : 0][epi], dim3(grid), dim3(kThreads), smem_bytes, stream, pair ? 2 : 1, p);
     count_launch();
