@@ -19,6 +19,7 @@ CASES = {
     "geglu320": lambda: bk.bench_linear(81920, 320, 2560, geglu=True),
     "attn2560": lambda: bk.bench_attn(32, 2560, 5),
     "attn640": lambda: bk.bench_attn(32, 640, 10),
+    "attnfusion": lambda: bk.bench_attn(16, 10240, 8, 20480),     # VAE level-2 dual-reference fusion attention
     "gn320": lambda: bk.bench_gn(32, 1, 2560, 320),
     "gn320t": lambda: bk.bench_gn(32, 16, 2560, 320),
 }

@@ -421,7 +421,7 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(kXsThreads, 3) tc_attn_xs_kernel(const AttnXsParams p) {
+__global__ void __launch_bounds__(kXsThreads, 4) tc_attn_xs_kernel(const AttnXsParams p) {
     tc::pdl_wait();   // no early launch_dependents (see temporal_attn_mma_kernel)
     __shared__ __align__(128) uint8_t sK[kXsMaxNT * 8 * 128];   // [key][64 halfs], 16-byte chunks XOR-swizzled by key & 7
     __shared__ __align__(128) uint8_t sV[kXsMaxNT * 8 * 128];
@@ -431,40 +431,67 @@ __global__ void __launch_bounds__(kXsThreads, 3) tc_attn_xs_kernel(const AttnXsP
     const int nk0 = (p.Lk[0] + 15) & ~15, nk1 = p.n_seg > 1 ? ((p.Lk[1] + 15) & ~15) : 0;
     const int ntot = (nk0 + nk1) >> 3, nt0 = nk0 >> 3;
 
-    // ---- K / V of both segments -> shared memory (rows past a segment's length are zero)
-    for (int ch = tid; ch < (nk0 + nk1) * 8; ch += kXsThreads) {
-        const int row = ch >> 3, c16 = ch & 7;
-        const int sgm = row >= nk0 ? 1 : 0;
-        const int r = row - (sgm ? nk0 : 0);
-        uint4 uk = make_uint4(0u, 0u, 0u, 0u), uv = uk;
-        if (r < p.Lk[sgm]) {
-            const long long kvb = qb / p.kv_div[sgm];
-            uk = *reinterpret_cast<const uint4*>(p.k[sgm] + (kvb * p.Lk[sgm] + r) * p.ldk[sgm] + head * 64 + c16 * 8);
-            uv = *reinterpret_cast<const uint4*>(p.v[sgm] + (kvb * p.Lk[sgm] + r) * p.ldv[sgm] + head * 64 + c16 * 8);
+    // ---- K / V of both segments -> shared memory (rows past a segment's length are zero).  All global loads of a
+    // thread are issued before its first shared store (load -> store per chunk serialised six L2 round trips).
+    {
+        constexpr int kMaxIt = (kXsMaxNT * 8 * 8 + kXsThreads - 1) / kXsThreads;   // 16-byte chunks per thread
+        uint4 uk[kMaxIt], uv[kMaxIt];
+#pragma unroll
+        for (int it = 0; it < kMaxIt; ++it) {
+            const int ch = tid + it * kXsThreads;
+            const int row = ch >> 3, c16 = ch & 7;
+            const int sgm = row >= nk0 ? 1 : 0;
+            const int r = row - (sgm ? nk0 : 0);
+            uk[it] = make_uint4(0u, 0u, 0u, 0u);
+            uv[it] = uk[it];
+            if (ch < (nk0 + nk1) * 8 && r < p.Lk[sgm]) {
+                const long long kvb = qb / p.kv_div[sgm];
+                uk[it] = *reinterpret_cast<const uint4*>(p.k[sgm] + (kvb * p.Lk[sgm] + r) * p.ldk[sgm] + head * 64 + c16 * 8);
+                uv[it] = *reinterpret_cast<const uint4*>(p.v[sgm] + (kvb * p.Lk[sgm] + r) * p.ldv[sgm] + head * 64 + c16 * 8);
+            }
         }
-        const int off = row * 128 + ((c16 ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(sK + off) = uk;
-        *reinterpret_cast<uint4*>(sV + off) = uv;
+#pragma unroll
+        for (int it = 0; it < kMaxIt; ++it) {
+            const int ch = tid + it * kXsThreads;
+            const int row = ch >> 3, c16 = ch & 7;
+            if (ch < (nk0 + nk1) * 8) {
+                const int off = row * 128 + ((c16 ^ (row & 7)) << 4);
+                *reinterpret_cast<uint4*>(sK + off) = uk[it];
+                *reinterpret_cast<uint4*>(sV + off) = uv[it];
+            }
+        }
     }
     __syncthreads();
     const uint32_t sK_a = tc::smem_u32(sK), sV_a = tc::smem_u32(sV);
     const float c = p.scale_log2;
     const int n_groups = (p.Lq + 15) >> 4;
 
-    for (int grp = (int)blockIdx.x * 4 + warp; grp < n_groups; grp += (int)gridDim.x * 4) {
+    // Q fragments (A operand, rows g8 and g8 + 8 of a 16-query group) straight from global memory; the NEXT group's are
+    // requested while this group's softmax / PV run (a warp's first HMMA sat on this load: 12 % of the samples)
+    auto load_q = [&](int grp, uint32_t (&dst)[4][4]) {
         const int r0 = grp * 16 + g8, r1 = r0 + 8;
-        const bool ok0 = r0 < p.Lq, ok1 = r1 < p.Lq;
+        const bool ok0 = grp < n_groups && r0 < p.Lq, ok1 = grp < n_groups && r1 < p.Lq;
         const __half* q0p = p.q + ((long long)qb * p.Lq + r0) * p.ldq + head * 64;
         const __half* q1p = p.q + ((long long)qb * p.Lq + r1) * p.ldq + head * 64;
-        uint32_t qa[4][4];
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             const int col = 16 * ks + 2 * t4;
-            qa[ks][0] = ok0 ? *reinterpret_cast<const uint32_t*>(q0p + col) : 0u;
-            qa[ks][1] = ok1 ? *reinterpret_cast<const uint32_t*>(q1p + col) : 0u;
-            qa[ks][2] = ok0 ? *reinterpret_cast<const uint32_t*>(q0p + col + 8) : 0u;
-            qa[ks][3] = ok1 ? *reinterpret_cast<const uint32_t*>(q1p + col + 8) : 0u;
+            dst[ks][0] = ok0 ? *reinterpret_cast<const uint32_t*>(q0p + col) : 0u;
+            dst[ks][1] = ok1 ? *reinterpret_cast<const uint32_t*>(q1p + col) : 0u;
+            dst[ks][2] = ok0 ? *reinterpret_cast<const uint32_t*>(q0p + col + 8) : 0u;
+            dst[ks][3] = ok1 ? *reinterpret_cast<const uint32_t*>(q1p + col + 8) : 0u;
         }
+    };
+    uint32_t qn[4][4];
+    load_q((int)blockIdx.x * 4 + warp, qn);
+    for (int grp = (int)blockIdx.x * 4 + warp; grp < n_groups; grp += (int)gridDim.x * 4) {
+        const int r0 = grp * 16 + g8, r1 = r0 + 8;
+        const bool ok0 = r0 < p.Lq, ok1 = r1 < p.Lq;
+        uint32_t qa[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qa[ks][i] = qn[ks][i];
         // ---- S = Q K^T: per n-tile two ldmatrix.x4 (d chunks 0-31, 32-63 of keys 8nt..8nt+7)
         float sacc[kXsMaxNT][4];
 #pragma unroll
@@ -487,6 +514,7 @@ __global__ void __launch_bounds__(kXsThreads, 3) tc_attn_xs_kernel(const AttnXsP
                 }
             }
         }
+        load_q(grp + (int)gridDim.x * 4, qn);
         // ---- two independent softmaxes: keys [0, Lk0) and [nk0, nk0 + Lk1); rows g8 (values 0,1) and g8 + 8 (values 2,3)
         float m00 = -INFINITY, m01 = -INFINITY, m10 = -INFINITY, m11 = -INFINITY;   // m<seg><row half>
 #pragma unroll

@@ -451,10 +451,10 @@ __device__ __forceinline__ f32x2 geglu_mul2(f32x2 a, f32x2 x) {
     unpk2(t, t0, t1);
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(h0) : "f"(t0));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(t1));
-    // Phi = 1 - h for x >= 0, h for x < 0
-    const float p0 = (x0 >> 31) ? h0 : 1.0f - h0;
-    const float p1 = (x1 >> 31) ? h1 : 1.0f - h1;
-    return mul2(mul2(a, x), pk2(p0, p1));
+    // Phi(x) = 1/2 + sign(x) (1/2 - h)  =>  x Phi(x) = x/2 + |x| (1/2 - h): no sign test, no select
+    const f32x2 half2 = pk2(0.5f, 0.5f);
+    const f32x2 xphi = fma2(ax, sub2(half2, pk2(h0, h1)), mul2(x, half2));
+    return mul2(a, xphi);
 }
 
 }  // namespace tc

@@ -531,9 +531,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 const int n2 = tn2 * p.TN + rn;
                 pre_row_ok = (rn < p.TN) && (x2 < p.oW) && (y2 < p.oH) && (n2 < p.oN);
                 const float2* ps = p.ln_stats + (((long long)n2 * p.oH + y2) * p.oW + x2) * p.ln_nslots;
+                // volatile asm: the compiler otherwise sinks these loads to their first use at the top of the next tile
+                // (4.4 % of the samples of the GEGLU launch sat there: profiles/r02_ncu_gemm_geglu_insitu.txt)
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    pre[i] = (pre_row_ok && i < p.ln_nslots) ? __ldg(ps + i) : make_float2(0.f, 0.f);
+                for (int i = 0; i < 4; ++i) {
+                    pre[i] = make_float2(0.f, 0.f);
+                    if (pre_row_ok && i < p.ln_nslots)
+                        asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(pre[i].x), "=f"(pre[i].y) : "l"(ps + i));
+                }
             }
             if (threadIdx.x == 64) { TC_TRACE(15, ti) }
             const uint32_t taddr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(q * 32) << 16);
