@@ -98,12 +98,20 @@ typedef struct {
    * separate statistics pass over the activation.  NULL = off. */
   float* row_stats;
   int row_stats_slots;
+  /* optional scratch for split-K (long K loops on few output tiles): caller-owned, any contents, at least
+   * TC_GEMM_WS_TICKET_BYTES of it zeroed ONCE before the first launch that uses it (the library leaves it zeroed).  NULL or too
+   * small: no split-K.  One workspace per stream (launches on one stream are ordered). */
+  void* workspace;
+  long long workspace_bytes;
 } TcConvGemm;
+#define TC_GEMM_WS_TICKET_BYTES (64 * 1024) /* head of the workspace: per-tile tickets (4 bytes each) */
 
 int tc_conv_gemm(const TcConvGemm* desc, void* stream);
 /* profiling aids: mode bits 1 = epilogue skips global stores, 2 = epilogue body skipped (results are then garbage),
  * 4 = record clock64() stamps per CTA / tile / warp role: [160 CTAs][32 tiles][16 slots] read back with *_read_gemm_trace */
 int tc_debug_set_gemm_mode(int mode);
+/* tests: {block_n, cta pair, k-slices, pipeline stages} of the calling thread's process' most recent tc_conv_gemm launch */
+int tc_debug_last_gemm_config(int* out4);
 int tc_debug_read_gemm_trace(unsigned long long* host_dst, int count);
 
 /* ------------------------------------------------------------------------------------------------

@@ -241,6 +241,43 @@ def test_conv3x3_emb_bias_and_skip(ops):
     _close(out, ref, "conv3x3 + emb + skip")
 
 
+@pytest.mark.parametrize("N,H,W,Cin,Cout,res", [(32, 5, 8, 1280, 1280, True), (32, 10, 16, 640, 640, False),
+                                                 (8, 5, 8, 2560, 1280, False), (3, 10, 16, 512, 96, True)])
+def test_conv3x3_split_k(ops, N, H, W, Cin, Cout, res):
+    """Few output tiles and a long K loop (the 1280- and 640-channel UNet levels): the launch splits K over otherwise idle
+    SMs; slices park fp32 partial tiles and the last one to finish sums them in slice order — the result must be
+    deterministic, identical run to run, and leave the ticket words ready for the next launch."""
+    x = _rand(N, H, W, Cin, seed=41).half()
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=42)
+    bias = _rand(Cout, seed=43).float()
+    emb = _rand(N, Cout, seed=44).half()
+    r = _rand(N, H, W, Cout, seed=45).half() if res else None
+    wp = _pack_conv_w(w)
+    outs = []
+    for rep in range(3):
+        out = torch.zeros(N, H, W, Cout, dtype=torch.float16, device=DEV)
+        ops.conv_gemm(x, (N, H, W, Cin), (H * W * Cin, W * Cin, Cin), wp, ops.TAPS_3x3, out, (N, H, W), Cout,
+                      bias=bias, bias2=emb, bias2_rows_per=H * W, res=r)
+        cfg = ops.last_gemm_config()
+        outs.append(out)
+        if rep == 0:
+            # another geometry in between: must find zeroed tickets and leave them zeroed
+            y = torch.zeros(1280, 640, dtype=torch.float16, device=DEV)
+            xa = _rand(1280, 10240, seed=46).half()
+            wa = _rand(640, 10240, scale=10240 ** -0.5, seed=47).half()
+            ops.linear(xa, wa, y, rows=1280, K=10240, n_cols=640)
+            cfg_lin = ops.last_gemm_config()
+            _close(y, xa.float() @ wa.float().t(), f"split-K linear 1280x10240x640 {cfg_lin}")
+    print("conv launch config:", cfg)
+    assert cfg["ksplit"] > 1 and cfg_lin["ksplit"] > 1, f"expected split-K launches: {cfg} {cfg_lin}"
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), "split-K result differs run to run"
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), bias, padding=1).permute(0, 2, 3, 1)
+    ref = ref + emb.float()[:, None, None, :]
+    if res:
+        ref = ref + r.float()
+    _close(outs[0], ref, f"split-K conv3x3 {N}x{H}x{W} {Cin}->{Cout} ksplit={cfg['ksplit']}")
+
+
 @pytest.mark.parametrize("B,T,H,W,C", [(2, 16, 5, 8, 128), (1, 16, 20, 32, 64), (1, 14, 10, 16, 128)])
 def test_temporal_conv(ops, B, T, H, W, C):
     """(3,1,1) Conv3d == 3-tap conv over T on the [B][T][HW][C] view."""

@@ -46,6 +46,8 @@ class TcConvGemm(C.Structure):
         ("ln_eps", C.c_float),
         ("row_stats", C.c_void_p),
         ("row_stats_slots", C.c_int),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_longlong),
     ]
 
 
@@ -67,6 +69,7 @@ _PROTOTYPES = {
     "tc_sm_count": (C.c_int, []),
     "tc_conv_gemm": (C.c_int, [C.POINTER(TcConvGemm), C.c_void_p]),
     "tc_debug_set_gemm_mode": (C.c_int, [C.c_int]),
+    "tc_debug_last_gemm_config": (C.c_int, [C.POINTER(C.c_int)]),
     "tc_debug_read_gemm_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "tc_groupnorm": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p,

@@ -81,6 +81,13 @@ struct alignas(64) GemmKParams {
     int BN;
     int raster;                     // tile order, see TC_DECODE_TILE
     FastDiv fd_nn, fd_mu, fd_x, fd_y, fd_xy, fd_b2;   // tiles_nn, M-tile units, tiles_x, tiles_y, tiles_x*tiles_y, bias2_rows_per
+    // split-K (long K loops on few output tiles, e.g. the 10x16 / 5x8 UNet levels where one wave of tiles leaves most SMs
+    // idle): work item = (tile, k-slice); every slice writes its fp32 partial tile to `ws_partial`, takes a ticket, and the
+    // LAST slice to arrive sums all partials in slice order (deterministic) and runs the normal epilogue
+    int ksplit, kb_per;             // k-slices per tile, k-blocks per slice
+    FastDiv fd_ks, fd_kc;           // ksplit, kc_per_tap
+    float* ws_partial;              // [total tiles][ksplit][128 rows][BN] floats
+    unsigned int* ws_ticket;        // [total tiles], zero between launches (the last slice resets it)
     int stage_bufs;                 // 1 or 2 output staging boxes (2: short-K launches, whose epilogue is the bottleneck)
     int n_cols;
     int stages;
@@ -170,6 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     uint64_t* bfree_bar = bfull_bar + 1;   // every MMA reading the resident B has retired
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bfree_bar + 1);
     // epilogue staging of the per-column vectors (bias, folded-LayerNorm u): [2 accumulators][bias 256 | u 256] floats
+    int* s_flag = reinterpret_cast<int*>(tmem_ptr_smem + 1);     // split-K: "this CTA holds the last slice of the tile"
     float* s_epi = reinterpret_cast<float*>(tmem_ptr_smem + 4);
     // output staging for the TMA-store epilogue: one 128-row x 32-column (64 B, 64B-swizzled) box per column group
     uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_epi + 1024) + 1023) & ~uintptr_t(1023));
@@ -231,8 +239,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int n_units = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int tiles_mu = kPair ? ((p.tiles_m + 1) >> 1) : p.tiles_m;
-    const int total_tiles = tiles_mu * p.tiles_nn;
-    const int kblocks = main_kblocks + p.res_kblocks;   // consumer view (residual k-blocks included)
+    const int tiles_mp = tiles_mu * (kPair ? 2 : 1);             // M tiles incl. the odd tail of a pair (workspace stride)
+    const int total_tiles = tiles_mu * p.tiles_nn * p.ksplit;   // work items: (output tile, k-slice), slice fastest
+    // work item -> output tile and the k-blocks of its slice (slice 0 also takes the residual k-blocks)
+#define TC_DECODE_WORK(wi)                                                          \
+    const int tile = fdiv((wi), p.fd_ks);                                           \
+    const int ks = (wi) - tile * p.ksplit;                                          \
+    const int kb_begin = ks * p.kb_per;                                             \
+    const int kb_end = (kb_begin + p.kb_per < main_kblocks) ? kb_begin + p.kb_per : main_kblocks; \
+    const int res_kb = (ks == 0) ? p.res_kblocks : 0;
     // tile -> (nt, mt) for this CTA; mt >= tiles_m (odd tail of a pair) decodes to out-of-range coordinates:
     // its TMA boxes are zero-filled and its rows are never stored
     // raster 0: N-tile-major (all M tiles of weight tile 0, then tile 1, ...: the resident-weight order);
@@ -261,7 +276,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             int cur_nt = -1;
             uint32_t bphase = 0;
             int ti = 0;
-            for (int tile = unit; tile < total_tiles; tile += n_units, ++ti) {
+            for (int wi = unit; wi < total_tiles; wi += n_units, ++ti) {
+                TC_DECODE_WORK(wi)
                 TC_DECODE_TILE(tile)
                 const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
                 if (lane == 0) { TC_TRACE(0, ti) }
@@ -286,9 +302,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     cur_nt = nt;
                     bphase ^= 1u;
                 }
-                for (int tap = 0; tap < p.taps; ++tap) {
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
+                    const int tap = fdiv(kb, p.fd_kc);
+                    const int kc = kb - tap * p.kc_per_tap;
                     const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap], an = n0 + p.tap_dn[tap];
-                    for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+                    {
                         tc::mbar_wait(&empty_bar[stage], phase ^ 1u);
                         if (tc::elect_one()) {
                             uint8_t* dA = sA + (size_t)stage * kAStageBytes;
@@ -316,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 }
                 // residual as extra k-blocks: acc[:, 64r:64r+64] += R[tile rows][64r:64r+64] @ I64  (TMA-coalesced, fully
                 // async; loading it from registers in the epilogue cost 32 us of a 81 us launch at M=81920, N=K=320)
-                for (int r = 0; r < p.res_kblocks; ++r) {
+                for (int r = 0; r < res_kb; ++r) {
                     tc::mbar_wait(&empty_bar[stage], phase ^ 1u);
                     if (tc::elect_one()) {
                         uint8_t* dA = sA + (size_t)stage * kAStageBytes;   // A slot only: B is the resident identity
@@ -353,7 +371,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             int cur_nt = -1;
             uint32_t bphase = 0;
             int ti = 0;
-            for (int tile = unit; tile < total_tiles; tile += n_units, ++ti) {
+            for (int wi = unit; wi < total_tiles; wi += n_units, ++ti) {
+                TC_DECODE_WORK(wi)
+                const int n_main = kb_end - kb_begin;
+                const int kblocks = n_main + res_kb;      // k-blocks of this work item (residual ones last)
                 if (p.b_resident && TC_TILE_NT(tile) != cur_nt) {
                     tc::mbar_wait(bfull_bar, bphase);
                     bphase ^= 1u;
@@ -368,7 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     tc::tc_fence_after();
                     if (kb == 0 && lane == 0) { TC_TRACE(3, ti) }
                     if (tc::elect_one()) {
-                        const int r = kb - main_kblocks;     // >= 0: residual k-block, N = 64 onto columns [64 r, 64 r + 64)
+                        const int r = kb - n_main;           // >= 0: residual k-block, N = 64 onto columns [64 r, 64 r + 64)
                         const uint64_t a_desc = a_desc0 + a_step * (uint64_t)stage;
                         const uint64_t b_desc = r >= 0 ? eye_desc : b_desc0 + b_step * (uint64_t)(p.b_resident ? kb : stage);
                         const uint32_t id = r >= 0 ? idesc_eye : idesc;
@@ -394,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 if (tc::elect_one()) {
                     if constexpr (kPair) tc::umma_commit_pair(&tfull_bar[acc]); else tc::umma_commit(&tfull_bar[acc]);
                     // last tile on this weight N-tile: tell the producer(s) when its MMAs have drained
-                    const int next = tile + n_units;
+                    const int next = wi + n_units;        // (weights are only resident without split-K: work item == tile)
                     if (p.b_resident && next < total_tiles && TC_TILE_NT(next) != cur_nt) {
                         if constexpr (kPair) tc::umma_commit_pair(bfree_bar); else tc::umma_commit(bfree_bar);
                     }
@@ -466,7 +487,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         float2 pre[4];                                     // next tile's partial slots (ln_nslots <= 4), raw
         const bool pre_ok = p.ln_stats != nullptr && p.ln_nslots >= 1 && p.ln_nslots <= 4;
         bool pre_row_ok = false;
-        for (int tile = unit; tile < total_tiles; tile += n_units, ++ti) {
+        for (int wi = unit; wi < total_tiles; wi += n_units, ++ti) {
+            TC_DECODE_WORK(wi)
+            (void)kb_begin; (void)kb_end; (void)res_kb;
             TC_DECODE_TILE(tile)
             const int x = tx * p.TW + rx, y = ty * p.TH + ry, n = tn * p.TN + rn;
             const bool row_ok = (rn < p.TN) && (x < p.oW) && (y < p.oH) && (n < p.oN);
@@ -521,8 +544,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             tc::tc_fence_after();
             if (threadIdx.x == 64) { TC_TRACE(6, ti) }
             if (restage) asm volatile("bar.sync 1, 256;" ::: "memory");       // staging visible to all epilogue warps
-            if (pre_ok && tile + n_units < total_tiles) {
-                const int tile2 = tile + n_units;
+            if (pre_ok && wi + n_units < total_tiles) {      // (folded LayerNorm launches never split K: work item == tile)
+                const int tile2 = wi + n_units;
                 const int nt2 = TC_TILE_NT(tile2);
                 const int mtu2 = p.raster ? fdiv(tile2, p.fd_nn) : tile2 - nt2 * tiles_mu;
                 const int mt2 = mtu2 * (kPair ? 2 : 1) + (int)rank;
@@ -543,7 +566,47 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             if (threadIdx.x == 64) { TC_TRACE(15, ti) }
             const uint32_t taddr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(q * 32) << 16);
 
-            if (g_tc_gemm_debug & 2) {
+            // ---- split-K: park this slice's fp32 accumulator tile, release TMEM, take a ticket; only the last slice of
+            // the tile to arrive goes on (it sums the slices in slice order: deterministic whatever the arrival order)
+            bool reduce = false, run_epilogue = true;
+            if (kEpi == 0 && p.ksplit > 1) {
+                // parked layout: [tile][slice][32-column chunk][4-float group 0..7][row 0..127] x 4 floats — the 32 rows of a
+                // warp write 512 contiguous bytes per instruction (row-major would touch 32 lines per instruction)
+                uint4* wslice = reinterpret_cast<uint4*>(p.ws_partial + ((long long)(nt * tiles_mp + mt) * p.ksplit + ks) * kBlockM * BN) + row;
+#pragma unroll 1
+                for (int jc = 0; jc < 4; ++jc) {
+                    const int c = (cg + 2 * jc) * 32;
+                    if (c >= BN) break;
+                    uint32_t r[32];
+                    tc::tmem_ld32(taddr + (uint32_t)c, r);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        __stcg(wslice + ((c >> 2) + i) * kBlockM, make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]));
+                }
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (kPair) tc::mbar_arrive_cluster(&tempty_bar[acc], 0); else tc::mbar_arrive(&tempty_bar[acc]);
+                }
+                __threadfence();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (threadIdx.x == 64) {
+                    unsigned int* tk = p.ws_ticket + (nt * tiles_mp + mt);
+                    const unsigned int t = atomicAdd(tk, 1u);
+                    const bool last = (t == (unsigned int)(p.ksplit - 1));
+                    if (last) *tk = 0u;                     // ready for the next launch (stream order)
+                    s_flag[0] = last ? 1 : 0;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                run_epilogue = s_flag[0] != 0;
+                reduce = true;
+                __threadfence();
+            }
+
+            if (!run_epilogue) {
+                // another slice finishes this tile
+            } else if (g_tc_gemm_debug & 2) {
                 // (profiling) accumulator is dropped: measures mainloop + handshake only
             } else if constexpr (kEpi != 2) {
                 // ---- TMEM -> registers -> swizzled smem box -> one TMA store per 32-column chunk.  Per-thread 16-byte
@@ -562,7 +625,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 uint32_t r[32];
                 uint32_t gr[4][16];                                    // GEGLU: {value, gate} x two 16-column halves of a chunk
                 tc::f32x2 rs_sum2 = 0ull, rs_sq2 = 0ull;
-                if (kEpi == 0 && cg * 32 < width) tc::tmem_ld32(taddr + (uint32_t)(cg * 32), r);
+                if (kEpi == 0 && !reduce && cg * 32 < width) tc::tmem_ld32(taddr + (uint32_t)(cg * 32), r);
 #pragma unroll 1
                 for (int jc = 0; jc < 4; ++jc) {
                     const int c = (cg + 2 * jc) * 32;
@@ -576,12 +639,29 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 #pragma unroll
                             for (int hh = 0; hh < 4; ++hh) rr[hh] = *reinterpret_cast<const uint4*>(rrow + c + hh * 8);
                         }
-                        tc::tmem_ld_wait();
                         tc::f32x2 v[16];
+                        if (!reduce) {
+                            tc::tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = tc::pk2u(r[2 * i], r[2 * i + 1]);
-                        // next chunk's accumulator read flies while this one is finished, staged and stored
-                        if (c + 64 < width) tc::tmem_ld32(taddr + (uint32_t)(c + 64), r);
+                            for (int i = 0; i < 16; ++i) v[i] = tc::pk2u(r[2 * i], r[2 * i + 1]);
+                            // next chunk's accumulator read flies while this one is finished, staged and stored
+                            if (c + 64 < width) tc::tmem_ld32(taddr + (uint32_t)(c + 64), r);
+                        } else {
+                            // split-K: sum the parked slices in slice order (L2 reads: other SMs wrote them)
+                            const uint4* wsrc = reinterpret_cast<const uint4*>(p.ws_partial + (long long)(nt * tiles_mp + mt) * p.ksplit * kBlockM * BN) +
+                                                (c >> 2) * kBlockM + row;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = 0ull;
+                            for (int sl = 0; sl < p.ksplit; ++sl) {
+                                const uint4* src4 = wsrc + (long long)sl * (kBlockM * BN / 4);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const uint4 u = __ldcg(src4 + i * kBlockM);
+                                    v[2 * i] = tc::add2(v[2 * i], tc::pk2u(u.x, u.y));
+                                    v[2 * i + 1] = tc::add2(v[2 * i + 1], tc::pk2u(u.z, u.w));
+                                }
+                            }
+                        }
                         // rstd*(acc - mean*u) + bias  ==  rstd*acc + (rm*u + bias), rm = -rstd*mean: two packed FMAs per pair
                         // (rstd = 1, rm = 0, u = 0 without a folded LayerNorm: exactly acc + bias).  The per-column vectors
                         // are read with 32-bit shared addresses: through generic pointers every read cost six 64-bit
@@ -869,10 +949,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     store_row16(orow + c, v, 16);
                 }
             }
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if constexpr (kPair) tc::mbar_arrive_cluster(&tempty_bar[acc], 0); else tc::mbar_arrive(&tempty_bar[acc]);
+            if (!(kEpi == 0 && p.ksplit > 1)) {      // (split-K released the accumulator right after parking it)
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (kPair) tc::mbar_arrive_cluster(&tempty_bar[acc], 0); else tc::mbar_arrive(&tempty_bar[acc]);
+                }
             }
             if (threadIdx.x == 64) { TC_TRACE(7, ti) }
             acc ^= 1;
@@ -898,11 +980,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 struct TileChoice {
     int bn;
     bool pair;
+    int ksplit;
 };
 
-TileChoice choose_tiles(int tiles_m, int n_cols, int kblocks, int forced_bn, int sms) {
+// max_ksplit > 1: the launch may split its K loop (plain TMA-store epilogue, workspace available)
+TileChoice choose_tiles(int tiles_m, int n_cols, int kblocks, int forced_bn, int sms, int max_ksplit, long long ws_floats) {
     const int n16 = (n_cols + 15) / 16 * 16;
-    TileChoice best{n16 <= 256 ? n16 : 256, false};
+    TileChoice best{n16 <= 256 ? n16 : 256, false, 1};
     double best_cost = 1e30;
     for (int bn = 256; bn >= 16; bn -= 16) {
         if (forced_bn > 0 && bn != forced_bn) continue;
@@ -921,14 +1005,29 @@ TileChoice choose_tiles(int tiles_m, int n_cols, int kblocks, int forced_bn, int
             const double ingest = (16384.0 + (double)bn * (pair ? 64.0 : 128.0)) / 52.0;
             double kb_cycles = tensor > ingest ? tensor : ingest;
             if (kb_cycles < 200.0) kb_cycles = 200.0;
-            const double tile_cost = (double)kblocks * kb_cycles + 1500.0 + 4.0 * bn;
-            const long long units = pair ? (long long)((tiles_m + 1) / 2) * tiles_n : (long long)tiles_m * tiles_n;
+            const long long tiles = pair ? (long long)((tiles_m + 1) / 2) * tiles_n : (long long)tiles_m * tiles_n;
             const int slots = pair ? sms / 2 : sms;
-            const long long waves = (units + slots - 1) / slots;
-            const double cost = (double)waves * tile_cost;
-            if (cost < best_cost) {
-                best_cost = cost;
-                best = TileChoice{bn, pair != 0};
+            for (int ks = 1; ks <= max_ksplit; ++ks) {
+                const int kb_per = (kblocks + ks - 1) / ks;
+                if (ks > 1) {
+                    // slices of >= 8 k-blocks, whole-tile workspace, and the bn must leave the TMA-store path applicable
+                    if (kb_per < 8 || (kb_per * (ks - 1)) >= kblocks) continue;
+                    const long long tiles_all = (long long)(pair ? 2 * ((tiles_m + 1) / 2) : tiles_m) * tiles_n;
+                    if (tiles_all * ks * 128 * bn > ws_floats || tiles_all * 4 > TC_GEMM_WS_TICKET_BYTES) continue;
+                    if (bn % 32 != 0 || n_cols % bn != 0) continue;
+                }
+                // split-K overhead, paid once in the launch's tail (earlier waves park under the next item's main loop): every
+                // slice parks 128 x bn floats in L2, a fence + ticket round trip, and the last slice reads ks of them back
+                // before the usual epilogue.  Measured (scripts/ksplit_ab.py, bn 256, 2 slices): ~10 us = ~20k cycles over
+                // the unsplit launch at equal k-blocks per CTA; a 5 % margin keeps marginal cases unsplit.
+                const double red = ks > 1 ? 22000.0 * (bn / 256.0) * (0.5 + 0.25 * ks) : 0.0;
+                const double tile_cost = (double)kb_per * kb_cycles + 1500.0 + 4.0 * bn;
+                const long long waves = (tiles * ks + slots - 1) / slots;
+                const double cost = ((double)waves * tile_cost + red) * (ks > 1 ? 1.05 : 1.0);
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    best = TileChoice{bn, pair != 0, ks};
+                }
             }
         }
     }
@@ -950,7 +1049,17 @@ extern "C" int tc_debug_read_gemm_trace(unsigned long long* host_dst, int count)
 #endif
 }
 
+static int g_last_cfg[4] = {0, 0, 0, 0};
+extern "C" int tc_debug_last_gemm_config(int* out4) {
+    if (!out4) return tc_host::fail(TC_ERR_INVALID, "tc_debug_last_gemm_config: null");
+    for (int i = 0; i < 4; ++i) out4[i] = g_last_cfg[i];
+    return TC_OK;
+}
+
+static int g_ksplit_cap = 0;   // profiling: bits 8..11 of the debug mode cap the k-slices of later launches (0 = heuristic)
 extern "C" int tc_debug_set_gemm_mode(int mode) {
+    g_ksplit_cap = (mode >> 8) & 15;
+    mode &= 255;
     return tc_host::check_cuda(cudaMemcpyToSymbol(g_tc_gemm_debug, &mode, sizeof(int)), "tc_debug_set_gemm_mode");
 }
 
@@ -998,10 +1107,12 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
             int TN = kBlockM / (TW * TH);
             if (TN > d->oN) TN = d->oN;
             if (TN < 1) continue;
-            if (TN > 1 && (TH != d->oH || TW != d->oW)) TN = 1;  // multi-frame boxes only over whole frames
+            // (a box may span several frames with only part of each: 10 x 16 frames tile as 16 x 2 x 4 — 40 full tiles for
+            // 32 frames where whole-frame or single-frame boxes need 64 tiles of 80 rows)
             const long long tiles = (long long)((d->oW + TW - 1) / TW) * ((d->oH + TH - 1) / TH) *
                                     ((d->oN + TN - 1) / TN);
-            if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && TW > bestTW)) {
+            if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && TW > bestTW) ||
+                (tiles == best_tiles && TW == bestTW && TH > bestTH)) {
                 best_tiles = tiles;
                 bestTW = TW;
                 bestTH = TH;
@@ -1021,10 +1132,21 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
     p.tiles_m = p.tiles_x * p.tiles_y * p.tiles_n;
     TC_CHECK_ARG((long long)d->oN * d->oH * d->oW < (1LL << 31), "tc_conv_gemm: more than 2^31 output rows");
     static const char* pair_env = getenv("TC_GEMM_PAIR");       // "0" / "1" force (A/B testing), unset = heuristic
-    TileChoice choice = choose_tiles(p.tiles_m, d->n_cols, d->taps * (d->a_C / kBlockK), BN, sm_count());
+    // split-K only with the plain TMA-store epilogue (no GEGLU, no LayerNorm fold, no row statistics) and a workspace
+    static const char* ksplit_env = getenv("TC_GEMM_KSPLIT");    // "1" disables, "2".."4" caps (A/B testing)
+    int max_ksplit = 4;
+    if (ksplit_env && ksplit_env[0] >= '1' && ksplit_env[0] <= '4') max_ksplit = ksplit_env[0] - '0';
+    if (g_ksplit_cap >= 1 && g_ksplit_cap <= 4) max_ksplit = g_ksplit_cap;
+    const long long ws_floats = d->workspace && d->workspace_bytes > TC_GEMM_WS_TICKET_BYTES
+                                    ? (d->workspace_bytes - TC_GEMM_WS_TICKET_BYTES) / 4 : 0;
+    if (geglu || d->ln_stats || d->row_stats || d->n_cols % 16 != 0 || ws_floats == 0 ||
+        (reinterpret_cast<uintptr_t>(d->workspace) & 15) != 0)
+        max_ksplit = 1;
+    TileChoice choice = choose_tiles(p.tiles_m, d->n_cols, d->taps * (d->a_C / kBlockK), BN, sm_count(), max_ksplit, ws_floats);
     BN = choice.bn;
     bool pair = choice.pair;
     if (pair_env) pair = (pair_env[0] == '1') && p.tiles_m >= 2;
+    p.ksplit = (pair == choice.pair) ? choice.ksplit : 1;
     p.BN = BN;
     p.tiles_nn = (d->n_cols + BN - 1) / BN;
     p.n_cols = d->n_cols;
@@ -1120,6 +1242,12 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
             }
         }
     }
+    if (!p.tma_store) p.ksplit = 1;
+    p.kb_per = (main_kblocks + p.ksplit - 1) / p.ksplit;
+    p.fd_ks = make_fastdiv((uint32_t)p.ksplit);
+    p.fd_kc = make_fastdiv((uint32_t)p.kc_per_tap);
+    p.ws_ticket = reinterpret_cast<unsigned int*>(d->workspace);
+    p.ws_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(d->workspace) + TC_GEMM_WS_TICKET_BYTES);
     const int stage_bytes = kAStageBytes + (pair ? BN / 2 : BN) * 128;
     // a second staging box pays off where the epilogue bounds the tile time (short K loops); long K loops would rather
     // have the 16 KiB as operand pipeline depth (conv 320->320 lost 10 % when it went from 5 to 4 stages)
@@ -1134,9 +1262,10 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
     {
         const long long units = pair ? pair_tiles : (long long)p.tiles_m * p.tiles_nn;
         const int slots = pair ? sm_count() / 2 : sm_count();
+        // (split-K launches never qualify: they are chosen when there are too FEW tiles per SM)
         const int bres_bytes = main_kblocks * (pair ? BN / 2 : BN) * 128;
         const int a_stages = (smem_budget - bres_bytes) / kAStageBytes;
-        if (bres_bytes < smem_budget && a_stages >= 5 && units >= 3LL * slots && !(bres_env && bres_env[0] == '0')) {
+        if (bres_bytes < smem_budget && a_stages >= 5 && units >= 3LL * slots && p.ksplit == 1 && !(bres_env && bres_env[0] == '0')) {
             p.b_resident = 1;
             stages = a_stages > 12 ? 12 : a_stages;
         }
@@ -1165,7 +1294,7 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
     }
     int units = pair ? sm_count() / 2 : sm_count();
     {
-        const long long total_units = pair ? pair_tiles : (long long)p.tiles_m * p.tiles_nn;
+        const long long total_units = (pair ? pair_tiles : (long long)p.tiles_m * p.tiles_nn) * p.ksplit;
         if (total_units < units) units = (int)total_units;
         // N-tile-fastest raster (see TC_DECODE_TILE).  With resident weights the unit count must be a multiple of tiles_nn
         // (then unit u keeps N tile u % tiles_nn for its whole life); give up at most ~4 % of the SMs for that.
@@ -1187,6 +1316,7 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
     p.fd_xy = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y));
     p.fd_b2 = make_fastdiv((uint32_t)p.bias2_rows_per);
     const int grid = pair ? 2 * units : units;
+    g_last_cfg[0] = BN, g_last_cfg[1] = pair ? 1 : 0, g_last_cfg[2] = p.ksplit, g_last_cfg[3] = stages;
     launch(kernels[pair ? 1 : 0][epi], dim3(grid), dim3(kThreads), smem_bytes, stream, pair ? 2 : 1, p);
     count_launch();
     TC_CHECK_LAUNCH("tc_gemm_kernel launch");

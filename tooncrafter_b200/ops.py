@@ -96,6 +96,9 @@ def conv_gemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, taps: Sequenc
     d.acc_scale = acc_scale
     d.flags = TC_EPI_GEGLU if geglu else 0
     d.block_n = block_n
+    ws = _gemm_ws(out.device)
+    d.workspace = ws.data_ptr()
+    d.workspace_bytes = ws.numel()
     if ln_stats is not None:
         d.ln_stats = ln_stats.data_ptr()
         d.ln_u = ln_u.data_ptr()
@@ -114,6 +117,28 @@ def linear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, rows: int, K:
     """out[rows][n] = x[rows][K] @ w[n][K].T (+ epilogue); x row stride ldx."""
     ldx = ldx if ldx is not None else K
     conv_gemm(x, (1, 1, rows, K), (rows * ldx, rows * ldx, ldx), w, TAPS_1x1, out, (1, 1, rows), n_cols, **kw)
+
+
+_GEMM_WS = {}
+GEMM_WS_BYTES = 96 << 20
+
+
+def _gemm_ws(device) -> torch.Tensor:
+    """Per-device split-K scratch of tc_conv_gemm (tickets at its head, zeroed once; launches on a stream are ordered)."""
+    if device.type != "cuda":
+        return torch.zeros(1, dtype=torch.uint8)
+    ws = _GEMM_WS.get(device)
+    if ws is None:
+        ws = torch.zeros(GEMM_WS_BYTES, dtype=torch.uint8, device=device)
+        _GEMM_WS[device] = ws
+    return ws
+
+
+def last_gemm_config() -> dict:
+    """(tests / profiling) tile configuration of the most recent tc_conv_gemm launch."""
+    out = (C.c_int * 4)()
+    check(_lib.load().tc_debug_last_gemm_config(out), "tc_debug_last_gemm_config")
+    return dict(block_n=out[0], pair=bool(out[1]), ksplit=out[2], stages=out[3])
 
 
 _GN_WS = {}
