@@ -16,7 +16,7 @@ def warm(fn, iters=20):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
-for frames, fps, hw, C in [(32, 16, 40, 1280), (32, 1, 40, 1280), (32, 16, 160, 1280), (32, 1, 160, 1280), (32, 16, 640, 640),
+for frames, fps, hw, C in [(32, 16, 40, 1280), (32, 1, 40, 1280), (32, 16, 160, 1280), (32, 1, 160, 1280), (32, 16, 640, 640), (32, 1, 640, 640),
                            (32, 16, 2560, 320), (32, 1, 2560, 320), (32, 16, 160, 2560), (16, 1, 320 * 512 // 4, 256)]:
     x = torch.randn(frames * hw, C, device="cuda").half(); y = torch.empty_like(x)
     g = torch.ones(C, device="cuda"); b = torch.zeros(C, device="cuda")

@@ -332,6 +332,41 @@ def test_groupnorm(ops, frames, fps, hw, C, silu, eps):
     _close(y, ref, "groupnorm")
 
 
+@pytest.mark.parametrize("frames,fps,hw,C,slice_ld,inplace", [
+    (32, 16, 2560, 320, 0, False),      # 52 MB, per-clip statistics
+    (32, 1, 2560, 320, 0, True),        # per-frame statistics, in place
+    (32, 16, 640, 640, 0, False),
+    (32, 1, 640, 640, 0, False),
+    (32, 16, 160, 1280, 2560, False),   # reads a channel slice of a wider tensor
+    (32, 16, 40, 1280, 0, True),
+    (3, 1, 7, 128, 0, False), (300, 1, 64, 64, 0, False),   # tiny rows / more stat groups than SMs
+])
+def test_groupnorm_full_size(ops, frames, fps, hw, C, slice_ld, inplace):
+    """GroupNorm + SiLU at the sizes the benchmark runs (both guidance branches of a 16-frame clip): strided input, in
+    place, repeated launches, results identical run to run (the cross-CTA reductions have a fixed order)."""
+    ldx = slice_ld or C
+    xw = (_rand(frames, hw, ldx, seed=51) * 1.5 + 0.3).half()
+    off = ldx - C
+    gamma = (_rand(C, seed=52) * 0.2 + 1.0).float()
+    beta = (_rand(C, seed=53) * 0.2).float()
+    xin = xw[..., off:].float()
+    outs = []
+    for rep in range(3):
+        if inplace:
+            y = xw.clone()
+            ops.groupnorm(y, y, gamma, beta, frames=frames, frames_per_stat=fps, hw=hw, C=C, silu=True, ldx=ldx, ldy=ldx,
+                          x_offset=off, y_offset=off)
+            outs.append(y[..., off:].clone())
+        else:
+            y = torch.zeros(frames, hw, C, dtype=torch.float16, device=DEV)
+            ops.groupnorm(xw, y, gamma, beta, frames=frames, frames_per_stat=fps, hw=hw, C=C, silu=True, ldx=ldx, x_offset=off)
+            outs.append(y)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), "GroupNorm differs run to run"
+    xr = xin.reshape(frames // fps, fps * hw, C).permute(0, 2, 1)
+    ref = F.silu(F.group_norm(xr, 32, gamma, beta, 1e-5)).permute(0, 2, 1).reshape(frames, hw, C)
+    _close(outs[0], ref, f"groupnorm {frames}/{fps} x {hw} x {C}")
+
+
 def test_gelu2d(ops):
     """Exact-erf GELU on a strided matrix, in place (Resampler feed-forward, resampler.py:27-34)."""
     rows, cols, ld = 300, 1024, 1280
