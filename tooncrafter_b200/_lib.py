@@ -106,6 +106,10 @@ EXPORTED_SYMBOLS = tuple(_PROTOTYPES.keys())
 
 
 def lib_path() -> Path:
+    import os
+    override = os.environ.get("TC_LIB_PATH")          # A/B runs of two builds on one box (scripts/, profiling only)
+    if override:
+        return Path(override).resolve()
     return Path(__file__).resolve().parent / "libtooncrafter_b200.so"
 
 
