@@ -107,12 +107,14 @@ typedef struct {
 #define TC_GEMM_WS_TICKET_BYTES (64 * 1024) /* head of the workspace: per-tile tickets (4 bytes each) */
 
 int tc_conv_gemm(const TcConvGemm* desc, void* stream);
-/* profiling aids: mode bits 1 = epilogue skips global stores, 2 = epilogue body skipped (results are then garbage),
+/* profiling aids, honoured by trace builds only (TC_BUILD_TRACE=1): mode bits 1 = epilogue skips global stores, 2 = epilogue body skipped (results are then garbage),
  * 4 = record clock64() stamps per CTA / tile / warp role: [160 CTAs][32 tiles][16 slots] read back with *_read_gemm_trace */
 int tc_debug_set_gemm_mode(int mode);
 /* tests: {block_n, cta pair, k-slices, pipeline stages} of the calling thread's process' most recent tc_conv_gemm launch */
 int tc_debug_last_gemm_config(int* out4);
 int tc_debug_read_gemm_trace(unsigned long long* host_dst, int count);
+/* trace builds only: clock64() stamps of tc_attn3_kernel's CTA (0,0,0), [24 key blocks][16 slots] (scripts/trace_attn.py) */
+int tc_debug_read_attn_trace(unsigned long long* host_dst, int count);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (+ optional SiLU), fp32 statistics, channels-last fp16 in/out.
@@ -156,7 +158,14 @@ int tc_attention(const TcAttention* desc, void* stream);
 int tc_temporal_attention(const void* q, const void* k, const void* v, long long ld, void* out, long long ldo,
                           int B, int T, int P, int heads, float scale, void* stream);
 
-/* row softmax of fp16 scores [rows][cols] scaled by `scale`, in place (VAE mid-block attention, d = 512:
+/* Fused single-head attention with a wide head (D = 64..512, D % 64 == 0, D % 128 == 0 above 256): the VAE mid-block
+ * AttnBlock (autoencoder_dualref.py:172-206: q/k/v 1x1 convs -> softmax(q k^T / sqrt(C)) v over the H*W tokens of a frame,
+ * C = 512 at full width; also the encoder's mid block).  q/k/v: [batches][L][D] halfs with row strides ldq/ldk/ldv (they
+ * may be channel slices of one fused qkv tensor), out: [batches][Lq][D] with row stride ldo.  Scores stay on chip. */
+int tc_attention_wide(const void* q, const void* k, const void* v, long long ldq, long long ldk, long long ldv,
+                      void* out, long long ldo, int batches, int Lq, int Lk, int D, float scale, void* stream);
+
+/* row softmax of fp16 scores [rows][cols] scaled by `scale`, in place (unfused form of the VAE mid-block attention, d = 512:
  * autoencoder_dualref.py:172-200) */
 int tc_softmax_rows(void* s, long long lds, int rows, int cols, float scale, void* stream);
 

@@ -1,4 +1,5 @@
-"""A/B of the attention kernels on the B200: second-generation kernel (TC_ATTN_IMPL=v2) vs the third generation with
+"""A/B of the attention kernels on the B200: third generation (one thread per query row) vs fourth (two threads per row;
+ATTN_AB_ALL=1 adds the second-generation kernel and the v3 polynomial fractions) with
 0..4 of every 8 exponential pairs on the FMA pipe (TC_ATTN_POLY).  For each variant: parity against torch fp32
 (max error, fraction outside rtol 1e-3 / atol 1e-4) on small / ragged shapes incl. data with large score ranges (forces
 the lazy-rescale path), then CUDA-event timings at the UNet level-0 and VAE fusion shapes.
@@ -36,13 +37,19 @@ def run(q, k, v, heads, kv_div=1):
 
 
 def variants():
-    yield "v2", dict(TC_ATTN_IMPL="v2")
-    for p in (0, 1, 2, 3, 4):
-        yield f"v3 poly={p}/8", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY=str(p))
+    if os.environ.get("ATTN_AB_ALL") == "1":
+        yield "v2", dict(TC_ATTN_IMPL="v2")
+        for p in (1, 2, 3, 4):
+            yield f"v3 poly={p}/8", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY=str(p))
+    yield "v3 p0 nopp", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY="0", TC_ATTN_PP="0")
+    for p in (0, 1, 2, 3):
+        yield f"v3 p{p} pp", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY=str(p), TC_ATTN_PP="1")
+    for p in (0, 1, 2, 3):
+        yield f"v4 p{p} pp", dict(TC_ATTN_IMPL="v4", TC_ATTN_POLY=str(p), TC_ATTN_PP="1")
 
 
 def set_env(e):
-    for k in ("TC_ATTN_IMPL", "TC_ATTN_POLY"):
+    for k in ("TC_ATTN_IMPL", "TC_ATTN_POLY", "TC_ATTN_PP"):
         os.environ.pop(k, None)
     os.environ.update(e)
 
@@ -141,16 +148,43 @@ def cross_timing():
                   f"{(4.0 * N * L * C) / ts[3] / 1e6:7.0f} GB/s (q + out)", flush=True)
 
 
+def wide():
+    """fused single-head attention, head dim 512 (VAE mid block): parity + time against the unfused GEMM / softmax path"""
+    for N, L, D in ((2, 300, 512), (2, 256, 256), (16, 2560, 512)):
+        qkv = torch.randn(N, L, 3 * D, device=DEV).half()
+        out = torch.zeros(N, L, D, dtype=torch.float16, device=DEV)
+        fn = lambda: ops.attention_wide(qkv, out, batches=N, L=L, D=D, scale=D ** -0.5, ld=3 * D, ldo=D, k_offset=D, v_offset=2 * D)
+        fn()
+        torch.cuda.synchronize()
+        q, k, v = (qkv[..., i * D:(i + 1) * D].float() for i in range(3))
+        ref = ((q @ k.transpose(-1, -2)) * D ** -0.5).softmax(-1) @ v
+        d = (out.float() - ref).abs()
+        viol = (d > 1e-4 + 1e-3 * ref.abs()).float().mean().item()
+        ts = []
+        for _ in range(7):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        fl = 4.0 * N * L * L * D
+        print(f"wide N={N} L={L} D={D}: max err {d.max().item():.3e} viol {viol:.2e} finite {torch.isfinite(out).all().item()} "
+              f"{ts[3] * 1e3:8.1f} us {fl / ts[3] / 1e9:7.1f} TF/s", flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--cross-only", action="store_true")
+    ap.add_argument("--wide-only", action="store_true")
     a = ap.parse_args()
     ap2 = a
     if getattr(a, "cross_only", False):
         cross_timing()
         sys.exit(0)
+    if a.wide_only:
+        wide()
+        sys.exit(0)
     good = parity()
     timing(a.quick)
-    cross_timing()
     print("PARITY_OK" if good else "PARITY_FAILED")

@@ -139,6 +139,13 @@ def temporal_attention(q, k, v, out, *, ld, ldo, B, T, P, heads, scale, q_offset
     _strided(out, (B, T, P, C), (T * P * ldo, P * ldo, ldo, 1), 0).copy_(o.half())
 
 
+def attention_wide(qkv, out, *, batches, L, D, scale, ld, ldo, q_offset=0, k_offset=0, v_offset=0, out_offset=0):
+    get = lambda off: _strided(qkv, (batches, L, D), (L * ld, ld, 1), off).float()
+    Q, K, V = get(q_offset), get(k_offset), get(v_offset)
+    att = ((Q @ K.transpose(-1, -2)) * scale).softmax(-1) @ V
+    _strided(out, (batches, L, D), (L * ldo, ldo, 1), out_offset).copy_(att.half())
+
+
 def softmax_rows(s, *, rows, cols, scale, lds=None):
     v = _view2d(s, rows, cols, lds if lds is not None else cols, 0)
     v.copy_((v.float() * scale).softmax(-1).half())
@@ -219,7 +226,7 @@ def ddim_step3(e_c, e_uc, e_img, x, noise, x_prev, pred_x0, coef, ws, *, B, n):
     ddim_step(e_c, e_uc, x, noise, x_prev, pred_x0, coef, ws, B=B, n=n, e_img=e_img)
 
 
-_TABLE = {f.__name__: f for f in (conv_gemm, groupnorm, row_stats, layernorm, attention, temporal_attention, softmax_rows,
+_TABLE = {f.__name__: f for f in (conv_gemm, groupnorm, row_stats, layernorm, attention, temporal_attention, softmax_rows, attention_wide,
                                   ncthw_to_cl, cl_to_ncthw, upsample2x, phase_split2, copy2d, add2d, time_embed,
                                   small_linear, ddim_step, ddim_step3, gelu2d)}
 

@@ -490,6 +490,33 @@ def test_temporal_attention(ops, B, T, P, heads):
     _close(out, ref, "temporal attention", ns_max=0.002)
 
 
+@pytest.mark.parametrize("N,L,D", [(2, 2560, 512), (3, 300, 512), (2, 256, 256), (1, 1000, 128), (2, 64, 64), (1, 130, 384)])
+def test_attention_wide(ops, N, L, D):
+    """VAE mid-block AttnBlock core (autoencoder_dualref.py:186-200): one head of D channels, q/k/v slices of a fused
+    qkv tensor; D = 512 (two CTAs per query tile, each half of the value channels) and the single-CTA widths, with ragged
+    query / key tiles.  Scores have the spread of the real layer (q, k ~ N(0, 1), scale D^-0.5)."""
+    qkv = _rand(N, L, 3 * D, seed=91).half()
+    out = torch.zeros(N, L, D, dtype=torch.float16, device=DEV)
+    ops.attention_wide(qkv, out, batches=N, L=L, D=D, scale=D ** -0.5, ld=3 * D, ldo=D, q_offset=0, k_offset=D, v_offset=2 * D)
+    q, k, v = (qkv[..., i * D:(i + 1) * D].float() for i in range(3))
+    ref = ((q @ k.transpose(-1, -2)) * D ** -0.5).softmax(-1) @ v
+    # P is rounded to fp16 for the PV product (as the reference's autocast bmm does): same bound as the d = 64 kernels
+    _close(out, ref, f"wide attention N={N} L={L} D={D}", ns_max=1e-3)
+
+
+def test_attention_wide_growing_maximum(ops):
+    """Keys whose scores grow along the sequence force the lazy O rescale (and its wait on the previous PV MMA)."""
+    N, L, D = 2, 1024, 512
+    qkv = _rand(N, L, 3 * D, seed=92)
+    qkv[..., D:2 * D] *= torch.linspace(0.2, 3.0, L, device=DEV)[None, :, None]
+    qkv = qkv.half()
+    out = torch.zeros(N, L, D, dtype=torch.float16, device=DEV)
+    ops.attention_wide(qkv, out, batches=N, L=L, D=D, scale=D ** -0.5, ld=3 * D, ldo=D, q_offset=0, k_offset=D, v_offset=2 * D)
+    q, k, v = (qkv[..., i * D:(i + 1) * D].float() for i in range(3))
+    ref = ((q @ k.transpose(-1, -2)) * D ** -0.5).softmax(-1) @ v
+    _close(out, ref, "wide attention, growing row maximum", ns_max=2e-3)
+
+
 def test_softmax_rows(ops):
     s = _rand(300, 2560, scale=3.0, seed=85).half()
     ref = (s.float() * 0.125).softmax(-1)

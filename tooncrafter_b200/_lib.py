@@ -71,6 +71,7 @@ _PROTOTYPES = {
     "tc_debug_set_gemm_mode": (C.c_int, [C.c_int]),
     "tc_debug_last_gemm_config": (C.c_int, [C.POINTER(C.c_int)]),
     "tc_debug_read_gemm_trace": (C.c_int, [C.c_void_p, C.c_int]),
+    "tc_debug_read_attn_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "tc_groupnorm": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p,
                                C.c_void_p]),
@@ -81,6 +82,8 @@ _PROTOTYPES = {
     "tc_temporal_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
                                         C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "tc_softmax_rows": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "tc_attention_wide": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong,
+                                    C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "tc_ncthw_to_cl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_float, C.c_void_p]),
     "tc_cl_to_ncthw": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
 ]
 if os.environ.get("TC_BUILD_TRACE") == "1":      # in-kernel role timeline for scripts/trace_gemm.py (slows the kernels)
-    NVCC_FLAGS.append("-DTC_GEMM_TRACE=1")
+    NVCC_FLAGS += ["-DTC_GEMM_TRACE=1", "-DTC_ATTN_TRACE=1"]
 
 
 def _nvcc() -> str:

@@ -106,6 +106,13 @@ struct alignas(64) GemmKParams {
     const float* ln_u;       // per column sum_k Wt[j][k]
 };
 
+// Profiling modes (tc_debug_set_gemm_mode) are honoured by TRACE builds only (TC_BUILD_TRACE=1, loaded through TC_LIB_PATH):
+// the production kernels do not read the mode word — it was a global load at the head of every tile's epilogue.
+#if defined(TC_GEMM_TRACE) && TC_GEMM_TRACE
+#define TC_DEBUG_MODE() g_tc_gemm_debug
+#else
+#define TC_DEBUG_MODE() 0
+#endif
 __device__ int g_tc_gemm_debug = 0;   // profiling aid (scripts/prof_epilogue.py): 1 = no global stores, 2 = no epilogue body,
                                       // 4 = record per-tile clock64() stamps of each warp role (scripts/trace_gemm.py)
 #if defined(TC_GEMM_TRACE) && TC_GEMM_TRACE
@@ -123,7 +130,7 @@ __device__ unsigned long long g_tc_gemm_trace[kTraceCtas * kTraceTiles * kTraceS
 #endif
 
 __device__ __forceinline__ void store_row16(__half* dst, const float (&v)[16], int ncols_valid) {
-    if (g_tc_gemm_debug & 1) return;
+    if (TC_DEBUG_MODE() & 1) return;
     if (ncols_valid >= 16) {
         uint4 u0, u1;
         __half2 h[8];
@@ -448,7 +455,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         // staging: one 128-row box per column group, or (warp_box) one 32-row box per warp
         const bool warp_box = p.warp_box != 0;
         uint8_t* stg = warp_box ? s_stage + (warp - 2) * 2048 : s_stage + cg * 8192;
-        const bool store_leader = warp_box ? (lane == 0) : ((warp == 2 + 4 * cg) && lane == 0);
+        // the warp that issues this thread's TMA stores (warp-uniform); the issuing LANE is picked with elect.sync at each
+        // use: behind a per-lane predicate (lane == 0) ptxas emits the store as a divergent R2UR / BRA.U.ANY loop — ~320
+        // cycles per chunk in the in-kernel timeline (profiles/r02_gemm_trace_k320.txt), as it did for the TMA loads in round 1
+        const bool store_warp = warp_box ? true : (warp == 2 + 4 * cg);
         const uint32_t stg_row = tc::smem_u32(stg) + (uint32_t)(warp_box ? lane : row) * 64u;
         const uint32_t stg_swz = (uint32_t)((row >> 1) & 3);
         // first row of this warp inside the tile box (warp_box: the origin of its store box)
@@ -606,7 +616,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 
             if (!run_epilogue) {
                 // another slice finishes this tile
-            } else if (g_tc_gemm_debug & 2) {
+            } else if (TC_DEBUG_MODE() & 2) {
                 // (profiling) accumulator is dropped: measures mainloop + handshake only
             } else if constexpr (kEpi != 2) {
                 // ---- TMEM -> registers -> swizzled smem box -> one TMA store per 32-column chunk.  Per-thread 16-byte
@@ -619,7 +629,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 const __half* b2row =
                     p.bias2 ? p.bias2 + (long long)(row_ok ? fdiv((int)m, p.fd_b2) : 0) * p.bias2_ld + (long long)nt * BN : nullptr;
                 const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
-                const int dbg = g_tc_gemm_debug;
+                const int dbg = TC_DEBUG_MODE();
                 const tc::f32x2 rstd2 = tc::pk2(ln_rstd, ln_rstd), rm2 = tc::pk2(ln_rm, ln_rm);
                 const tc::f32x2 scale2 = tc::pk2(p.acc_scale, p.acc_scale);
                 uint32_t r[32];
@@ -762,8 +772,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     uint8_t* stg_b = stg + buf * 16384u;
                     const uint32_t stg_row_b = stg_row + buf * 16384u;
                     ++n_stores;
-                    if (store_leader) {
-                        if (p.stage_bufs == 2) tc::bulk_wait_group_read<1>(); else tc::bulk_wait_group_read<0>();
+                    if (store_warp) {
+                        if (tc::elect_one()) {
+                            if (p.stage_bufs == 2) tc::bulk_wait_group_read<1>(); else tc::bulk_wait_group_read<0>();
+                        }
                     }
                     if (warp_box) __syncwarp();
                     else if (cg == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -783,13 +795,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     else if (cg == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
                     else asm volatile("bar.sync 3, 128;" ::: "memory");
                     if (threadIdx.x == 64 && jc == 0) { TC_TRACE(12, ti) }
-                    if (store_leader && !(dbg & 1)) {
+                    if (store_warp && !(dbg & 1)) {
                         if (warp_box) {
                             if (warp_rows_in_tile) {
-                                tc::tma_store_4d(stg_b, &p.tmOw, nt * width + c, x0 + wx, y0 + wy, n0 + wn);
-                                tc::bulk_commit_group();
+                                if (tc::elect_one()) {
+                                    tc::tma_store_4d(stg_b, &p.tmOw, nt * width + c, x0 + wx, y0 + wy, n0 + wn);
+                                    tc::bulk_commit_group();
+                                }
                             }
-                        } else {
+                        } else if (tc::elect_one()) {
                             tc::tma_store_4d(stg_b, &p.tmO, nt * width + c, x0, y0, n0);
                             tc::bulk_commit_group();
                         }
@@ -964,7 +978,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 #undef TC_DECODE_TILE
 #undef TC_TILE_NT
 
-    if (p.tma_store && warp >= 2 && lane == 0) tc::bulk_wait_group<0>();
+    if (p.tma_store && warp >= 2) {
+        if (tc::elect_one()) tc::bulk_wait_group<0>();      // the lane that committed the store groups
+    }
     tc::tc_fence_before();
     if constexpr (kPair) tc::cluster_sync_all(); else __syncthreads();   // the peer may still read our smem / barriers
     if (warp == 2) {

@@ -214,6 +214,17 @@ def temporal_attention(q, k, v, out, *, ld: int, ldo: int, B: int, T: int, P: in
                                     _stream()), "tc_temporal_attention")
 
 
+def attention_wide(qkv: torch.Tensor, out: torch.Tensor, *, batches: int, L: int, D: int, scale: float, ld: int, ldo: int,
+                   q_offset: int = 0, k_offset: int = 0, v_offset: int = 0, out_offset: int = 0) -> None:
+    """Single-head attention with head dim D (<= 512) over [batches][L] tokens; q / k / v are channel slices (element
+    offsets) of one tensor with row stride `ld` (VAE mid-block AttnBlock, autoencoder_dualref.py:172-206)."""
+    _req_half(qkv, "qkv"); _req_half(out, "out")
+    lib = _lib.load()
+    base = qkv.data_ptr()
+    check(lib.tc_attention_wide(base + 2 * q_offset, base + 2 * k_offset, base + 2 * v_offset, ld, ld, ld,
+                                out.data_ptr() + 2 * out_offset, ldo, batches, L, L, D, scale, _stream()), "tc_attention_wide")
+
+
 def softmax_rows(s: torch.Tensor, *, rows: int, cols: int, scale: float, lds: Optional[int] = None) -> None:
     lib = _lib.load()
     check(lib.tc_softmax_rows(s.data_ptr(), lds if lds is not None else cols, rows, cols, scale, _stream()),
