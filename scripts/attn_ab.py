@@ -1,5 +1,5 @@
-"""A/B of the attention kernels on the B200: third generation (one thread per query row) vs fourth (two threads per row;
-ATTN_AB_ALL=1 adds the second-generation kernel and the v3 polynomial fractions) with
+"""A/B of the attention kernels on the B200: third generation with its options (exponential-phase token, start stagger;
+ATTN_AB_ALL=1 adds the second-generation kernel and the polynomial fractions) with
 0..4 of every 8 exponential pairs on the FMA pipe (TC_ATTN_POLY).  For each variant: parity against torch fp32
 (max error, fraction outside rtol 1e-3 / atol 1e-4) on small / ragged shapes incl. data with large score ranges (forces
 the lazy-rescale path), then CUDA-event timings at the UNet level-0 and VAE fusion shapes.
@@ -41,15 +41,14 @@ def variants():
         yield "v2", dict(TC_ATTN_IMPL="v2")
         for p in (1, 2, 3, 4):
             yield f"v3 poly={p}/8", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY=str(p))
-    yield "v3 p0 nopp", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY="0", TC_ATTN_PP="0")
-    for p in (0, 1, 2, 3):
-        yield f"v3 p{p} pp", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY=str(p), TC_ATTN_PP="1")
-    for p in (0, 1, 2, 3):
-        yield f"v4 p{p} pp", dict(TC_ATTN_IMPL="v4", TC_ATTN_POLY=str(p), TC_ATTN_PP="1")
+    yield "v3 p0", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY="0")
+    yield "v3 p1", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY="1")
+    yield "v3 p0 token", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY="0", TC_ATTN_PP="1")
+    yield "v3 p0 stagger", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY="0", TC_ATTN_STAGGER="1200")
 
 
 def set_env(e):
-    for k in ("TC_ATTN_IMPL", "TC_ATTN_POLY", "TC_ATTN_PP"):
+    for k in ("TC_ATTN_IMPL", "TC_ATTN_POLY", "TC_ATTN_PP", "TC_ATTN_STAGGER"):
         os.environ.pop(k, None)
     os.environ.update(e)
 

@@ -646,7 +646,7 @@ __global__ void softmax_rows_kernel(__half* __restrict__ s, long long lds, int r
 
 using namespace tc_host;
 
-int tc_attention_v3(const TcAttention* d, int poly_of_8, int gen, cudaStream_t stream);   // tc_attn3.cu
+int tc_attention_v3(const TcAttention* d, int poly_of_8, cudaStream_t stream);   // tc_attn3.cu
 int tc_attention_xs(const TcAttention* d, cudaStream_t stream);                    // tc_attn3.cu (small K/V, 1-2 segments)
 
 // TC_ATTN_IMPL=v2 keeps single-segment problems on the second-generation kernel below (A/B runs);
@@ -654,10 +654,6 @@ int tc_attention_xs(const TcAttention* d, cudaStream_t stream);                 
 static int attn_impl_v3() {
     const char* e = getenv("TC_ATTN_IMPL");
     return !(e && e[0] == 'v' && e[1] == '2');
-}
-static int attn_gen() {                     // TC_ATTN_IMPL=v3 / v4 picks the tcgen05 kernel generation (default v3)
-    const char* e = getenv("TC_ATTN_IMPL");
-    return (e && e[0] == 'v' && e[1] == '4') ? 4 : 3;
 }
 static int attn_poly() {
     const char* e = getenv("TC_ATTN_POLY");
@@ -673,7 +669,7 @@ extern "C" int tc_attention(const TcAttention* d, void* stream_v) {
     if (d->n_seg == 1 && attn_impl_v3()) {
         TC_CHECK_ARG(d->k[0] && d->v[0] && d->Lk[0] > 0 && d->kv_div[0] > 0, "tc_attention: bad kv segment");
         TC_CHECK_ARG(d->ldk[0] % 8 == 0 && d->ldv[0] % 8 == 0, "tc_attention: kv strides must be multiples of 8");
-        return tc_attention_v3(d, attn_poly(), attn_gen(), stream);
+        return tc_attention_v3(d, attn_poly(), stream);
     }
     if (attn_impl_v3()) {
         // short K/V (the 77 text + 16 image tokens of the cross attentions): resident-K/V kernel when the shape fits

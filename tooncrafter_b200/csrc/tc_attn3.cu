@@ -23,7 +23,7 @@ constexpr int kQTile = 128;
 constexpr int kKVTile = 128;
 constexpr int kTileBytes = 128 * 64 * 2;   // 16 KiB: [128 rows][64 halfs], 128B-swizzled
 constexpr int kStages = 3;                 // K and V rings
-constexpr int kThreads = 320;              // warps 0-3 / 4-7 softmax warpgroups, 8 MMA issuer, 9 TMA producer
+constexpr int kThreads = 352;              // warps 0-3 / 4-7 softmax warpgroups, 8 / 10 MMA issuers (tile 0 / 1), 9 TMA producer
 constexpr uint32_t kTmemCols = 512;        // S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) P0 [384,448) P1 [448,512)
 constexpr uint32_t kTmemO = 256, kTmemP = 384;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: P <= 2^8 fits fp16 with room, sums stay in fp32
@@ -35,6 +35,7 @@ struct alignas(64) Attn3Params {
     long long ldo;
     float scale_log2;
     int pingpong;   // the two query tiles take turns on the exponential phase (named-barrier token), see the softmax loops
+    int stagger;    // cycles by which query tile 1 starts late (keeps the two tiles' exponential phases out of step)
 };
 
 typedef unsigned long long u64;
@@ -120,6 +121,76 @@ __device__ __forceinline__ void exp2_poly2(u64 x2, float& e0, float& e1) {
     e1 = __uint_as_float(p1 + (t1 << 23));
 }
 
+// MMA issuer of ONE query tile (one warp per tile, one elected lane issues): S_w(g+1) = Q_w K(g+1)^T as soon as the tile's
+// softmax threads hold S_w(g) in registers, then O_w += P_w(g) V(g) with P as the TMEM A operand.  One warp used to issue
+// for both tiles: at ~100 cycles of issue work per tcgen05.mma (R2UR descriptor traffic on the uniform datapath) 24 small
+// MMAs + 6 commits per key block kept that warp busy ~2200 of the ~2900 cycles a block took and coupled the two tiles' timing
+// (in-kernel timeline, profiles/r02_attn_trace.txt).  K / V ring stages are released by BOTH issuers (barrier count =
+// number of active tiles); tcgen05 ops of different issuers are unordered, which is fine: the tiles share no TMEM.
+struct AttnBars {
+    uint64_t *bar_q, *k_full, *k_free, *v_full, *v_free, *s_full, *s_free, *p_ready, *o_full;
+};
+__device__ __forceinline__ void attn_issue_tile(const Attn3Params& p, const AttnBars& b, int w, int G, uint32_t tmem_base, uint32_t sQ_a,
+                                                uint32_t sK_a, uint32_t sV_a) {
+    auto block_nk = [&](int g) {
+        const int left = p.Lk - g * kKVTile;
+        return left < kKVTile ? ((left + 15) & ~15) : kKVTile;
+    };
+    const uint64_t qd = tc::umma_desc_sw128(sQ_a + (uint32_t)w * kTileBytes);
+    const uint64_t kd0 = tc::umma_desc_sw128(sK_a);
+    const uint32_t s_tmem = tmem_base + (uint32_t)w * 128, o_tmem = tmem_base + kTmemO + (uint32_t)w * 64,
+                   p_tmem = tmem_base + kTmemP + (uint32_t)w * 64;
+    auto issue_s = [&](int st, int nk) {          // called by ONE elected lane
+        const uint32_t idesc = tc::umma_idesc_f16(128, (uint32_t)nk, 0, 0);
+        const uint64_t kd = kd0 + (uint64_t)(st * (kTileBytes >> 4));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc::umma_f16(s_tmem, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc, k != 0);
+        tc::umma_commit(&b.s_full[w]);
+        tc::umma_commit(&b.k_free[st]);
+    };
+    // one elected lane runs the whole loop, waits included (per-block ELECT / reconvergence and vector-register descriptor
+    // arithmetic were a good part of the ~100 cycles of issue work per MMA)
+    if (tc::elect_one()) {
+        tc::mbar_wait(b.bar_q, 0);
+        tc::mbar_wait(&b.k_full[0], 0);
+        tc::tc_fence_after();
+        issue_s(0, block_nk(0));
+        const uint32_t idesc_o = tc::umma_idesc_f16(128, 64, 0, 1);       // B (= V tile [keys][64]) MN-major
+        const uint64_t vd0 = tc::umma_desc_sw128(sV_a);
+        int st = 0;
+        uint32_t ph = 0;
+        for (int g = 0; g < G; ++g) {
+            const int nk = block_nk(g);
+            if (g + 1 < G) {
+                const int st1 = (st + 1 == kStages) ? 0 : st + 1;
+                const uint32_t ph1 = (st + 1 == kStages) ? (ph ^ 1u) : ph;
+                tc::mbar_wait(&b.k_full[st1], ph1);
+                tc::mbar_wait(&b.s_free[w], (uint32_t)(g & 1));
+                tc::tc_fence_after();
+                TC_ATRACE(12 + w, g)
+                issue_s(st1, block_nk(g + 1));
+            }
+            tc::mbar_wait(&b.v_full[st], ph);
+            tc::mbar_wait(&b.p_ready[w], (uint32_t)(g & 1));
+            tc::tc_fence_after();
+            TC_ATRACE(14 + w, g)
+            const uint64_t vd = vd0 + (uint64_t)(st * (kTileBytes >> 4));
+            if (nk == kKVTile) {
+#pragma unroll
+                for (int t = 0; t < kKVTile / 16; ++t)
+                    tc::umma_f16_ts(o_tmem, p_tmem + (uint32_t)(t * 8), vd + (uint64_t)(t * 128), idesc_o, (g != 0 || t != 0) ? 1u : 0u);
+            } else {
+                for (int t = 0; t < nk / 16; ++t)
+                    tc::umma_f16_ts(o_tmem, p_tmem + (uint32_t)(t * 8), vd + (uint64_t)(t * 128), idesc_o, (g != 0 || t != 0) ? 1u : 0u);
+            }
+            tc::umma_commit(&b.o_full[w]);
+            tc::umma_commit(&b.v_free[st]);
+            if (++st == kStages) { st = 0; ph ^= 1u; }
+        }
+    }
+    __syncwarp();
+}
+
 // kPoly of every 8 consecutive PAIRS of exponentials go to the polynomial, the rest to MUFU.EX2.
 template <int kPoly>
 __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_constant__ Attn3Params p) {
@@ -155,9 +226,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_cons
         tc::mbar_init(bar_q, 1);
         for (int i = 0; i < kStages; ++i) {
             tc::mbar_init(&k_full[i], 1);
-            tc::mbar_init(&k_free[i], 1);
+            tc::mbar_init(&k_free[i], (uint32_t)ntiles);      // released by every active tile's MMA issuer
             tc::mbar_init(&v_full[i], 1);
-            tc::mbar_init(&v_free[i], 1);
+            tc::mbar_init(&v_free[i], (uint32_t)ntiles);
         }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&s_full[i], 1);
@@ -205,73 +276,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_cons
             __syncwarp();
             if (++st == kStages) { st = 0; ph ^= 1u; }
         }
-    } else if (warp == 8) {
-        // ------------------------------------------------------------------------------ MMA issuer
-        const uint32_t sQ_a = tc::smem_u32(sQ), sK_a = tc::smem_u32(sK), sV_a = tc::smem_u32(sV);
-        auto block_nk = [&](int g) {
-            const int left = p.Lk - g * kKVTile;
-            return left < kKVTile ? ((left + 15) & ~15) : kKVTile;
-        };
-        // S_w = Q_w K^T for the key block in ring slot `st`; called by ONE elected lane
-        auto issue_s = [&](int w, int st, int nk) {
-            const uint32_t idesc = tc::umma_idesc_f16(128, (uint32_t)nk, 0, 0);
-            const uint64_t qd = tc::umma_desc_sw128(sQ_a + (uint32_t)w * kTileBytes);
-            const uint64_t kd = tc::umma_desc_sw128(sK_a + (uint32_t)st * kTileBytes);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                tc::umma_f16(tmem_base + (uint32_t)w * 128, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc, k != 0);
-            tc::umma_commit(&s_full[w]);
-        };
-        tc::mbar_wait(bar_q, 0);
-        tc::mbar_wait(&k_full[0], 0);
-        tc::tc_fence_after();
-        if (tc::elect_one()) {
-            const int nk = block_nk(0);
-            for (int w = 0; w < ntiles; ++w) issue_s(w, 0, nk);
-            tc::umma_commit(&k_free[0]);
+    } else if (warp == 8 || warp == 10) {
+        // ------------------------------------------------------------------------------ MMA issuers (one per query tile)
+        const int w = warp == 8 ? 0 : 1;
+        if (w < ntiles) {
+            const AttnBars b{bar_q, k_full, k_free, v_full, v_free, s_full, s_free, p_ready, o_full};
+            attn_issue_tile(p, b, w, G, tmem_base, tc::smem_u32(sQ), tc::smem_u32(sK), tc::smem_u32(sV));
         }
-        __syncwarp();
-        int st = 0;
-        uint32_t ph = 0;
-        for (int g = 0; g < G; ++g) {
-            const int nk = block_nk(g);
-            // ---- S of the NEXT block as soon as the softmax warps have pulled this block's S into registers
-            if (g + 1 < G) {
-                const int st1 = (st + 1 == kStages) ? 0 : st + 1;
-                const uint32_t ph1 = (st + 1 == kStages) ? (ph ^ 1u) : ph;
-                const int nk1 = block_nk(g + 1);
-                tc::mbar_wait(&k_full[st1], ph1);
-                for (int w = 0; w < ntiles; ++w) {
-                    tc::mbar_wait(&s_free[w], (uint32_t)(g & 1));
-                    tc::tc_fence_after();
-                    if (tc::elect_one()) {
-                        TC_ATRACE(12 + w, g)
-                        issue_s(w, st1, nk1);
-                        if (w == ntiles - 1) tc::umma_commit(&k_free[st1]);
-                    }
-                    __syncwarp();
-                }
-            }
-            // ---- O_w += P_w V for this block (P from tensor memory)
-            tc::mbar_wait(&v_full[st], ph);
-            for (int w = 0; w < ntiles; ++w) {
-                tc::mbar_wait(&p_ready[w], (uint32_t)(g & 1));
-                tc::tc_fence_after();
-                if (tc::elect_one()) {
-                    TC_ATRACE(14 + w, g)
-                    const uint32_t idesc_o = tc::umma_idesc_f16(128, 64, 0, 1);   // B (= V tile [keys][64]) MN-major
-                    const uint64_t vd = tc::umma_desc_sw128(sV_a + (uint32_t)st * kTileBytes);
-                    for (int t = 0; t < nk / 16; ++t)
-                        tc::umma_f16_ts(tmem_base + kTmemO + (uint32_t)w * 64, tmem_base + kTmemP + (uint32_t)w * 64 + (uint32_t)(t * 8),
-                                        vd + (uint64_t)(t * 128), idesc_o, (g != 0 || t != 0) ? 1u : 0u);
-                    tc::umma_commit(&o_full[w]);
-                    if (w == ntiles - 1) tc::umma_commit(&v_free[st]);
-                }
-                __syncwarp();
-            }
-            if (++st == kStages) { st = 0; ph ^= 1u; }
-        }
-    } else if ((warp >> 2) < ntiles) {
+    } else if (warp < 8 && (warp >> 2) < ntiles) {
         // ------------------------------------------------------------------------------ softmax warpgroups
         const int w = warp >> 2;
         const int row = tid & 127;
@@ -285,6 +297,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_cons
         const bool pp = p.pingpong != 0 && ntiles == 2;
         const uint32_t tok_zero = tc::smem_u32(s_tok), tok_sink = tc::smem_u32(s_tok + 1 + tid);
         if (pp && w == 1) asm volatile("bar.arrive 14, 256;" ::: "memory");   // tile 0 goes first
+        if (w == 1 && p.stagger > 0 && ntiles == 2) {
+            // Both tiles share the 16 MUFU lanes.  Started together they stay in step (exponentials of both at half rate,
+            // then both in the TMEM / maximum / PV part with MUFU idle); started half a block apart one tile's
+            // exponentials run under the other's PV round trip.  Nothing pulls the tiles back into step afterwards.
+            const long long t0 = clock64();
+            while (clock64() - t0 < (long long)p.stagger) { }
+        }
         for (int g = 0; g < G; ++g) {
             const int kv_left = p.Lk - g * kKVTile;
             const int nvalid = kv_left < kKVTile ? kv_left : kKVTile;
@@ -439,321 +458,6 @@ int launch_attn3(const Attn3Params& p, dim3 grid, size_t smem_bytes, cudaStream_
 }
 
 
-// ===================================================================================== fourth generation
-// Same data path as tc_attn3_kernel (S, O, P in tensor memory, P as the TMEM A operand, early S hand-back, lazy rescale),
-// but TWO threads per query row: the 128-key row of S is split into two 64-key halves owned by two warps of the same TMEM
-// lane quadrant, so sixteen softmax warps (four per scheduler) are in flight instead of eight.  With one row per thread
-// the two warps of a scheduler ran in phase (both reading TMEM / reducing the maximum, then both on MUFU) and the XU pipe
-// idled 30 % of the time (profiles/r02_ncu_attn2560.txt: XU 66 %, tensor 31.6 %); four shorter warps interleave.  The
-// halves exchange their block maximum (and, at the end, their row sums) through shared memory with a 64-thread named
-// barrier per (query tile, lane quadrant); each half rescales / normalises / stores its own 32 columns of O.
-constexpr int kThreads4 = 576;             // warps 0-15 softmax: quadrant = warp & 3, tile = (warp >> 2) & 1, half = warp >> 3;
-                                           // warp 16 MMA issuer, warp 17 TMA producer
-
-template <int kPoly>
-__global__ void __launch_bounds__(kThreads4, 1) tc_attn4_kernel(const __grid_constant__ Attn3Params p) {
-    tc::pdl_launch_dependents();
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                  // 2 tiles
-    uint8_t* sK = smem + 2 * kTileBytes;                 // kStages
-    uint8_t* sV = smem + (2 + kStages) * kTileBytes;     // kStages
-    float* xch = reinterpret_cast<float*>(smem + (2 + 2 * kStages) * kTileBytes);   // [parity 2][tile 2][half 2][128 rows]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 2 * 2 * 128);
-    uint64_t* bar_q = bars + 0;
-    uint64_t* k_full = bars + 1;                 // [kStages]
-    uint64_t* k_free = k_full + kStages;
-    uint64_t* v_full = k_free + kStages;
-    uint64_t* v_free = v_full + kStages;
-    uint64_t* s_full = v_free + kStages;         // [2] per query tile: S accumulator written
-    uint64_t* s_free = s_full + 2;               // [2] 256 arrivals: S row is in registers
-    uint64_t* p_ready = s_free + 2;              // [2] 256 arrivals: P row is in TMEM
-    uint64_t* o_full = p_ready + 2;              // [2] PV MMA of the block retired
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 2);
-    float* s_tok = reinterpret_cast<float*>(bars + 32);   // [0] = 0.0f, [1 + tid] sink: data fences of the exponential-phase token
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int q0 = blockIdx.x * 2 * kQTile;
-    const int head = blockIdx.y;
-    const int qb = blockIdx.z;
-    const int ntiles = (q0 + kQTile < p.Lq) ? 2 : 1;
-    const int G = (p.Lk + kKVTile - 1) / kKVTile;
-
-    if (tid == 0) {
-        s_tok[0] = 0.f;
-        tc::mbar_init(bar_q, 1);
-        for (int i = 0; i < kStages; ++i) {
-            tc::mbar_init(&k_full[i], 1);
-            tc::mbar_init(&k_free[i], 1);
-            tc::mbar_init(&v_full[i], 1);
-            tc::mbar_init(&v_free[i], 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&s_full[i], 1);
-            tc::mbar_init(&s_free[i], 256);
-            tc::mbar_init(&p_ready[i], 256);
-            tc::mbar_init(&o_full[i], 1);
-        }
-        tc::fence_mbar_init();
-    }
-    if (warp == 16) {
-        tc::tmem_alloc(tmem_ptr_smem, kTmemCols);
-        tc::tmem_relinquish();
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-    tc::pdl_wait();   // prologue (barriers, TMEM) overlapped the predecessor; Q/K/V are its results
-
-    if (warp == 17) {
-        // ------------------------------------------------------------------------------ TMA producer
-        if (tc::elect_one()) {
-            tc::tma_prefetch_desc(&p.tmQ);
-            tc::tma_prefetch_desc(&p.tmK);
-            tc::tma_prefetch_desc(&p.tmV);
-            tc::mbar_arrive_expect_tx(bar_q, (uint32_t)(ntiles * kTileBytes));
-            for (int w = 0; w < ntiles; ++w) tc::tma_load_3d(sQ + w * kTileBytes, &p.tmQ, bar_q, head * 64, q0 + w * kQTile, qb);
-        }
-        __syncwarp();
-        const int kvb = qb / p.kv_div;
-        int st = 0;
-        uint32_t ph = 0;
-        for (int g = 0; g < G; ++g) {
-            tc::mbar_wait(&k_free[st], ph ^ 1u);
-            if (tc::elect_one()) {
-                tc::mbar_arrive_expect_tx(&k_full[st], kTileBytes);
-                tc::tma_load_3d(sK + st * kTileBytes, &p.tmK, &k_full[st], head * 64, g * kKVTile, kvb);
-            }
-            __syncwarp();
-            tc::mbar_wait(&v_free[st], ph ^ 1u);
-            if (tc::elect_one()) {
-                tc::mbar_arrive_expect_tx(&v_full[st], kTileBytes);
-                tc::tma_load_3d(sV + st * kTileBytes, &p.tmV, &v_full[st], head * 64, g * kKVTile, kvb);
-            }
-            __syncwarp();
-            if (++st == kStages) { st = 0; ph ^= 1u; }
-        }
-    } else if (warp == 16) {
-        // ------------------------------------------------------------------------------ MMA issuer (as in v3)
-        const uint32_t sQ_a = tc::smem_u32(sQ), sK_a = tc::smem_u32(sK), sV_a = tc::smem_u32(sV);
-        auto block_nk = [&](int g) {
-            const int left = p.Lk - g * kKVTile;
-            return left < kKVTile ? ((left + 15) & ~15) : kKVTile;
-        };
-        auto issue_s = [&](int w, int st, int nk) {
-            const uint32_t idesc = tc::umma_idesc_f16(128, (uint32_t)nk, 0, 0);
-            const uint64_t qd = tc::umma_desc_sw128(sQ_a + (uint32_t)w * kTileBytes);
-            const uint64_t kd = tc::umma_desc_sw128(sK_a + (uint32_t)st * kTileBytes);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                tc::umma_f16(tmem_base + (uint32_t)w * 128, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc, k != 0);
-            tc::umma_commit(&s_full[w]);
-        };
-        tc::mbar_wait(bar_q, 0);
-        tc::mbar_wait(&k_full[0], 0);
-        tc::tc_fence_after();
-        if (tc::elect_one()) {
-            const int nk = block_nk(0);
-            for (int w = 0; w < ntiles; ++w) issue_s(w, 0, nk);
-            tc::umma_commit(&k_free[0]);
-        }
-        __syncwarp();
-        int st = 0;
-        uint32_t ph = 0;
-        for (int g = 0; g < G; ++g) {
-            const int nk = block_nk(g);
-            if (g + 1 < G) {
-                const int st1 = (st + 1 == kStages) ? 0 : st + 1;
-                const uint32_t ph1 = (st + 1 == kStages) ? (ph ^ 1u) : ph;
-                const int nk1 = block_nk(g + 1);
-                tc::mbar_wait(&k_full[st1], ph1);
-                for (int w = 0; w < ntiles; ++w) {
-                    tc::mbar_wait(&s_free[w], (uint32_t)(g & 1));
-                    tc::tc_fence_after();
-                    if (tc::elect_one()) {
-                        issue_s(w, st1, nk1);
-                        if (w == ntiles - 1) tc::umma_commit(&k_free[st1]);
-                    }
-                    __syncwarp();
-                }
-            }
-            tc::mbar_wait(&v_full[st], ph);
-            for (int w = 0; w < ntiles; ++w) {
-                tc::mbar_wait(&p_ready[w], (uint32_t)(g & 1));
-                tc::tc_fence_after();
-                if (tc::elect_one()) {
-                    const uint32_t idesc_o = tc::umma_idesc_f16(128, 64, 0, 1);   // B (= V tile [keys][64]) MN-major
-                    const uint64_t vd = tc::umma_desc_sw128(sV_a + (uint32_t)st * kTileBytes);
-                    for (int t = 0; t < nk / 16; ++t)
-                        tc::umma_f16_ts(tmem_base + kTmemO + (uint32_t)w * 64, tmem_base + kTmemP + (uint32_t)w * 64 + (uint32_t)(t * 8),
-                                        vd + (uint64_t)(t * 128), idesc_o, (g != 0 || t != 0) ? 1u : 0u);
-                    tc::umma_commit(&o_full[w]);
-                    if (w == ntiles - 1) tc::umma_commit(&v_free[st]);
-                }
-                __syncwarp();
-            }
-            if (++st == kStages) { st = 0; ph ^= 1u; }
-        }
-    } else if (((warp >> 2) & 1) < ntiles) {
-        // ------------------------------------------------------------------------------ softmax: 2 threads per query row
-        const int w = (warp >> 2) & 1;           // query tile
-        const int hf = warp >> 3;                // key half of the block: keys [64 hf, 64 hf + 64)
-        const int qd = warp & 3;                 // TMEM lane quadrant
-        const int row = qd * 32 + (tid & 31);
-        const uint32_t lane_off = ((uint32_t)(qd * 32)) << 16;
-        const uint32_t tmem_s = tmem_base + (uint32_t)w * 128 + (uint32_t)hf * 64 + lane_off;
-        const uint32_t tmem_o = tmem_base + kTmemO + (uint32_t)w * 64 + (uint32_t)hf * 32 + lane_off;
-        const uint32_t tmem_p = tmem_base + kTmemP + (uint32_t)w * 64 + (uint32_t)hf * 32 + lane_off;
-        float* x_mine = xch + (w * 2 + hf) * 128 + row;           // + parity * 512
-        float* x_peer = xch + (w * 2 + (hf ^ 1)) * 128 + row;
-        const int bar_id = 1 + w * 4 + qd;                         // the two warps that share these 32 rows
-        const float c = p.scale_log2;
-        const u64 c2 = pack2(c, c);
-        float m_run = -INFINITY, l_run = 0.f;
-        const bool pp = p.pingpong != 0 && ntiles == 2;
-        const uint32_t tok_zero = tc::smem_u32(s_tok), tok_sink = tc::smem_u32(s_tok + 1 + tid);
-        if (pp && w == 1) asm volatile("bar.arrive 14, 512;" ::: "memory");   // tile 0 goes first
-        for (int g = 0; g < G; ++g) {
-            const int kv_left = p.Lk - g * kKVTile - hf * 64;
-            const int nvalid = kv_left < 64 ? kv_left : 64;        // may be <= 0: this half of the ragged block is empty
-            tc::mbar_wait(&s_full[w], (uint32_t)(g & 1));
-            tc::tc_fence_after();
-            uint32_t s[64];
-            tc::tmem_ld32(tmem_s, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-            tc::tmem_ld32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-            tc::tmem_ld_wait();
-            tc::tc_fence_before();
-            tc::mbar_arrive(&s_free[w]);               // the tensor core may overwrite S with the next block now
-            if (nvalid < 64) {
-#pragma unroll
-                for (int i = 0; i < 64; ++i)
-                    if (i >= nvalid) s[i] = 0xff800000u;   // -inf
-            }
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < 64; i += 8) {
-                mx0 = max3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-                mx1 = max3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-                mx2 = max3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
-                mx3 = max3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
-            }
-            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-            // ---- the row's block maximum: exchange with the thread that owns the other 64 keys (slot by block parity:
-            // a slot is rewritten two blocks later, after its reader passed the next block's barrier)
-            x_mine[(g & 1) * 512] = mx;
-            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-            const float m_new = fmaxf(m_run, fmaxf(mx, x_peer[(g & 1) * 512]));
-            // ---- lazy rescale (both halves take the same decision from the same numbers)
-            const bool grow = (m_new - m_run) * c > kRescaleThreshold;    // first block: (x - -inf) = +inf -> true
-            const float m_use = grow ? m_new : m_run;
-            if (g > 0) {
-                tc::mbar_wait(&o_full[w], (uint32_t)((g - 1) & 1));       // PV of the previous block retired: P and O are ours
-                tc::tc_fence_after();
-                if (__any_sync(0xffffffffu, grow)) {
-                    const float alpha = ex2((m_run - m_use) * c);          // 1 for the rows that keep their maximum
-                    l_run *= alpha;
-#pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {                       // this half's 32 columns of O
-                        uint32_t r[16];
-                        tc::tmem_ld16(tmem_o + (uint32_t)(cc * 16), r);
-                        tc::tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                        tc::tmem_st16(tmem_o + (uint32_t)(cc * 16), r);
-                    }
-                    tc::tmem_st_wait();
-                }
-            }
-            m_run = m_use;
-            float nm = -m_use * c;
-            if (pp) {                                                        // this tile's turn on the MUFU lanes (see v3)
-                asm volatile("bar.sync %0, 512;" ::"r"(14 + w) : "memory");
-                float z;
-                asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(z) : "r"(tok_zero) : "memory");
-                nm += z;
-            }
-            const u64 nm2 = pack2(nm, nm);
-            u64 sum_a = 0ull, sum_b = 0ull;
-            uint32_t pk[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {             // pair j = keys 2j, 2j + 1 of this half
-                const u64 x = fma2(pack2(__uint_as_float(s[2 * j]), __uint_as_float(s[2 * j + 1])), c2, nm2);
-                float e0, e1;
-                if ((j & 7) < kPoly) {
-                    exp2_poly2(x, e0, e1);
-                } else {
-                    float x0, x1;
-                    unpack2(x, x0, x1);
-                    e0 = ex2(x0);
-                    e1 = ex2(x1);
-                }
-                if (j & 1) sum_b = add2(sum_b, pack2(e0, e1));
-                else sum_a = add2(sum_a, pack2(e0, e1));
-                pk[j] = pack_h2(e0, e1);
-            }
-            float a0, a1, b0, b1;
-            unpack2(sum_a, a0, a1);
-            unpack2(sum_b, b0, b1);
-            const float l_blk = (a0 + a1) + (b0 + b1);
-            if (pp) {
-                asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"(tok_sink), "f"(l_blk) : "memory");
-                asm volatile("bar.arrive %0, 512;" ::"r"(14 + (w ^ 1)) : "memory");
-            }
-            tc::tmem_st32(tmem_p, &pk[0]);
-            tc::tmem_st_wait();
-            tc::tc_fence_before();
-            tc::mbar_arrive(&p_ready[w]);
-            l_run += l_blk;
-        }
-        // ---- epilogue: row sum = both halves' sums (fixed order: half 0 + half 1), O / l -> fp16 -> global
-        x_mine[(G & 1) * 512] = l_run;
-        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-        const float l_peer = x_peer[(G & 1) * 512];
-        const float l_tot = hf == 0 ? l_run + l_peer : l_peer + l_run;
-        tc::mbar_wait(&o_full[w], (uint32_t)((G - 1) & 1));
-        tc::tc_fence_after();
-        const float inv_l = 1.0f / l_tot;
-        const int qrow = q0 + w * kQTile + row;
-        __half* dst = p.out + ((long long)qb * p.Lq + qrow) * p.ldo + head * 64 + hf * 32;
-        uint32_t r[32];
-        tc::tmem_ld32(tmem_o, r);
-        tc::tmem_ld_wait();
-        if (qrow < p.Lq) {
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                uint4 u;
-                u.x = pack_h2(__uint_as_float(r[8 * q4 + 0]) * inv_l, __uint_as_float(r[8 * q4 + 1]) * inv_l);
-                u.y = pack_h2(__uint_as_float(r[8 * q4 + 2]) * inv_l, __uint_as_float(r[8 * q4 + 3]) * inv_l);
-                u.z = pack_h2(__uint_as_float(r[8 * q4 + 4]) * inv_l, __uint_as_float(r[8 * q4 + 5]) * inv_l);
-                u.w = pack_h2(__uint_as_float(r[8 * q4 + 6]) * inv_l, __uint_as_float(r[8 * q4 + 7]) * inv_l);
-                reinterpret_cast<uint4*>(dst)[q4] = u;
-            }
-        }
-    }
-
-    tc::tc_fence_before();
-    __syncthreads();
-    if (warp == 16) {
-        tc::tc_fence_after();
-        tc::tmem_dealloc(tmem_base, kTmemCols);
-    }
-}
-
-template <int kPoly>
-int launch_attn4(const Attn3Params& p, dim3 grid, size_t smem_bytes, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        int rc = tc_host::check_cuda(cudaFuncSetAttribute(tc_attn4_kernel<kPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                          (int)smem_bytes),
-                                     "cudaFuncSetAttribute(tc_attn4_kernel)");
-        if (rc) return rc;
-        attr_set = true;
-    }
-    tc_host::launch(tc_attn4_kernel<kPoly>, grid, dim3(kThreads4), smem_bytes, stream, 1, p);
-    return 0;
-}
 
 // ===================================================================================== small-KV cross attention
 // Text + image cross attention of the spatial transformers (lvdm/modules/attention.py:126-142 / 196-207): every query
@@ -1004,8 +708,7 @@ extern "C" int tc_debug_read_attn_trace(unsigned long long* host_dst, int count)
 
 // Single-segment attention through the third-generation kernel.  `poly_of_8`: how many of every 8 exponential pairs
 // run on the FMA pipe (0 = all MUFU).  Called by tc_attention (tc_attn.cu) after it validated the descriptor.
-// `gen`: 3 = one thread per query row (tc_attn3_kernel), 4 = two threads per row (tc_attn4_kernel).
-int tc_attention_v3(const TcAttention* d, int poly_of_8, int gen, cudaStream_t stream) {
+int tc_attention_v3(const TcAttention* d, int poly_of_8, cudaStream_t stream) {
     Attn3Params p;
     memset(&p, 0, sizeof(p));
     const uint32_t box[3] = {64, 128, 1};
@@ -1034,25 +737,14 @@ int tc_attention_v3(const TcAttention* d, int poly_of_8, int gen, cudaStream_t s
     p.ldo = d->ldo;
     p.scale_log2 = d->scale * 1.4426950408889634f;
     {
-        const char* pp_env = getenv("TC_ATTN_PP");   // "0" disables the exponential-phase token (A/B testing)
-        p.pingpong = !(pp_env && pp_env[0] == '0');
+        const char* pp_env = getenv("TC_ATTN_PP");   // "1" enables the exponential-phase token (A/B testing; measured no gain)
+        p.pingpong = (pp_env && pp_env[0] == '1');
+        const char* sg_env = getenv("TC_ATTN_STAGGER");   // cycles (A/B testing)
+        p.stagger = sg_env ? atoi(sg_env) : 0;
     }
-    const size_t smem_bytes = (size_t)(2 + 2 * kStages) * kTileBytes + 1024 + 512 + 4096 + (gen == 4 ? 4096 : 0);
+    const size_t smem_bytes = (size_t)(2 + 2 * kStages) * kTileBytes + 1024 + 512 + 4096;
     dim3 grid((d->Lq + 2 * kQTile - 1) / (2 * kQTile), d->heads, d->q_batches);
     int rc;
-    if (gen == 4) {
-        switch (poly_of_8) {
-            case 0: rc = launch_attn4<0>(p, grid, smem_bytes, stream); break;
-            case 1: rc = launch_attn4<1>(p, grid, smem_bytes, stream); break;
-            case 2: rc = launch_attn4<2>(p, grid, smem_bytes, stream); break;
-            case 4: rc = launch_attn4<4>(p, grid, smem_bytes, stream); break;
-            default: rc = launch_attn4<3>(p, grid, smem_bytes, stream); break;
-        }
-        if (rc) return rc;
-        count_launch();
-        TC_CHECK_LAUNCH("tc_attn4_kernel");
-        return TC_OK;
-    }
     switch (poly_of_8) {
         case 0: rc = launch_attn3<0>(p, grid, smem_bytes, stream); break;
         case 1: rc = launch_attn3<1>(p, grid, smem_bytes, stream); break;

@@ -10,12 +10,17 @@
 //     CTA's flops; the pair executes 1.5x the minimal flops and needs no cross-CTA exchange).  D <= 256: one CTA.
 //   * TMEM: S/P buffer 0 [0,128), S/P buffer 1 [128,256), O [256, 256 + D_cta).  P (fp16) overwrites the first 64 columns of
 //     the S buffer it was computed from and is the TMEM A operand of the PV MMA (as in tc_attn3_kernel); S(g+2) is issued
-//     into a buffer right behind the PV(g) that reads it — tcgen05 MMAs of one issuing thread execute in order.
+//     into that buffer once PV(g) has retired.
 //   * Q (128 x D, 16 KiB per 64-channel k-block) stays in shared memory; K k-blocks and V sub-tiles ([128 keys][64 channels])
-//     stream through ONE ring of 16 KiB slots in exactly the order the MMA warp consumes them:
-//     K(0) K(1) | V(0) K(2) | V(1) K(3) | ...
+//     stream through TWO rings of 16 KiB slots, each with one producer warp and one consumer (issuer) warp walking it in
+//     order.  (One shared ring walked "by position" by two consumers is wrong: mbarrier waits are by phase PARITY, and a
+//     consumer that skips the other's slots can reach a slot two fills early, where the parity matches again — stale tiles
+//     under load.)
 //   * warps 0-3: softmax, one query row per thread (fp32, online, lazy rescale: O is only touched when a row maximum grew
-//     by more than 2^8; otherwise PV(g-1) is awaited AFTER block g's exponentials); warp 4: MMA issuer; warp 5: TMA producer.
+//     by more than 2^8; otherwise PV(g-1) is awaited AFTER block g's exponentials); warp 4: issuer of the S MMAs; warp 5:
+//     TMA producer of Q and K; warp 6: issuer of the PV MMAs; warp 7: TMA producer of V.  Two issuers because issuing is
+//     the bottleneck of small MMAs: ~100 cycles of issue work per tcgen05.mma against 32-64 cycles of execution (64 MMAs
+//     per key block at D = 512; one issuer ran 7200 cycles per block against 3072 tensor cycles).
 //   The kernel is tensor-bound by construction (per 128-key block 3072 tensor cycles vs 1024 MUFU cycles at D = 512).
 //
 // Algorithmic flops = 4 * N * Lq * Lk * D (the S recompute is not counted).
@@ -27,7 +32,7 @@ namespace {
 constexpr int kQTile = 128;
 constexpr int kKVTile = 128;
 constexpr int kTileBytes = 128 * 64 * 2;   // 16 KiB: [128 rows][64 halfs], 128B-swizzled
-constexpr int kThreads = 192;
+constexpr int kThreads = 256;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemO = 256;
 constexpr float kRescaleThreshold = 8.0f;
@@ -37,7 +42,7 @@ struct alignas(64) AttnWideParams {
     int Lq, Lk;
     int kq;          // D / 64: k-blocks of the score contraction
     int vs;          // value sub-tiles (64 channels each) per CTA
-    int ring;        // ring slots
+    int rk, rv;      // slots of the K ring / of the V ring
     __half* out;
     long long ldo;
     float scale_log2;
@@ -80,17 +85,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn_wide_kernel(const __grid_
     tc::pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int KQ = p.kq, VS = p.vs, R = p.ring;
+    const int KQ = p.kq, VS = p.vs, RK = p.rk, RV = p.rv;
     uint8_t* sQ = smem;                                   // KQ tiles
-    uint8_t* sR = smem + (size_t)KQ * kTileBytes;         // R ring slots
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + (size_t)R * kTileBytes);
+    uint8_t* sKr = smem + (size_t)KQ * kTileBytes;        // RK slots: K k-blocks
+    uint8_t* sVr = sKr + (size_t)RK * kTileBytes;         // RV slots: V sub-tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sVr + (size_t)RV * kTileBytes);
     uint64_t* bar_q = bars + 0;
-    uint64_t* ring_full = bars + 1;          // [R]
-    uint64_t* ring_free = ring_full + R;     // [R]
-    uint64_t* s_full = ring_free + R;        // [2] S(g) written (buffer g & 1)
+    uint64_t* k_full = bars + 1;             // [RK]
+    uint64_t* k_free = k_full + RK;          // [RK]
+    uint64_t* v_full = k_free + RK;          // [RV]
+    uint64_t* v_free = v_full + RV;          // [RV]
+    uint64_t* s_full = v_free + RV;          // [2] S(g) written (buffer g & 1)
     uint64_t* p_ready = s_full + 2;          // [2] 128 arrivals: P(g) is in TMEM, O rescaled if it had to be
-    uint64_t* o_done = p_ready + 2;          // [1] PV(g) retired (one phase per key block)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 1);
+    uint64_t* o_done = p_ready + 2;          // [2] PV(g) retired (buffer g & 1: one phase per TWO key blocks, so a waiter
+                                             //     can never fall two phases behind — parity waits would alias)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 2);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -101,15 +110,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn_wide_kernel(const __grid_
 
     if (tid == 0) {
         tc::mbar_init(bar_q, 1);
-        for (int i = 0; i < R; ++i) {
-            tc::mbar_init(&ring_full[i], 1);
-            tc::mbar_init(&ring_free[i], 1);
+        for (int i = 0; i < RK; ++i) {
+            tc::mbar_init(&k_full[i], 1);
+            tc::mbar_init(&k_free[i], 1);
+        }
+        for (int i = 0; i < RV; ++i) {
+            tc::mbar_init(&v_full[i], 1);
+            tc::mbar_init(&v_free[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&s_full[i], 1);
             tc::mbar_init(&p_ready[i], 128);
         }
-        tc::mbar_init(o_done, 1);
+        tc::mbar_init(&o_done[0], 1);
+        tc::mbar_init(&o_done[1], 1);
         tc::fence_mbar_init();
     }
     if (warp == 4) {
@@ -128,101 +142,102 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn_wide_kernel(const __grid_
     };
 
     if (warp == 5) {
-        // ------------------------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------------------------ TMA producer: Q, then the K ring
         if (tc::elect_one()) {
             tc::tma_prefetch_desc(&p.tmQ);
             tc::tma_prefetch_desc(&p.tmK);
-            tc::tma_prefetch_desc(&p.tmV);
             tc::mbar_arrive_expect_tx(bar_q, (uint32_t)(KQ * kTileBytes));
             for (int kb = 0; kb < KQ; ++kb) tc::tma_load_3d(sQ + kb * kTileBytes, &p.tmQ, bar_q, kb * 64, q0, nb);
+            int slot = 0;
+            uint32_t ph = 0;
+            for (int g = 0; g < G; ++g)
+                for (int kb = 0; kb < KQ; ++kb) {
+                    tc::mbar_wait(&k_free[slot], ph ^ 1u);
+                    tc::mbar_arrive_expect_tx(&k_full[slot], kTileBytes);
+                    tc::tma_load_3d(sKr + slot * kTileBytes, &p.tmK, &k_full[slot], kb * 64, g * kKVTile, nb);
+                    if (++slot == RK) { slot = 0; ph ^= 1u; }
+                }
         }
         __syncwarp();
-        int slot = 0;
-        uint32_t ph = 0;
-        auto load_k = [&](int g) {
-            for (int kb = 0; kb < KQ; ++kb) {
-                tc::mbar_wait(&ring_free[slot], ph ^ 1u);
-                if (tc::elect_one()) {
-                    tc::mbar_arrive_expect_tx(&ring_full[slot], kTileBytes);
-                    tc::tma_load_3d(sR + slot * kTileBytes, &p.tmK, &ring_full[slot], kb * 64, g * kKVTile, nb);
+    } else if (warp == 7) {
+        // ------------------------------------------------------------------------------ TMA producer: the V ring
+        if (tc::elect_one()) {
+            tc::tma_prefetch_desc(&p.tmV);
+            int slot = 0;
+            uint32_t ph = 0;
+            for (int g = 0; g < G; ++g)
+                for (int j = 0; j < VS; ++j) {
+                    tc::mbar_wait(&v_free[slot], ph ^ 1u);
+                    tc::mbar_arrive_expect_tx(&v_full[slot], kTileBytes);
+                    tc::tma_load_3d(sVr + slot * kTileBytes, &p.tmV, &v_full[slot], (half_idx * VS + j) * 64, g * kKVTile, nb);
+                    if (++slot == RV) { slot = 0; ph ^= 1u; }
                 }
-                __syncwarp();
-                if (++slot == R) { slot = 0; ph ^= 1u; }
-            }
-        };
-        auto load_v = [&](int g) {
-            for (int j = 0; j < VS; ++j) {
-                tc::mbar_wait(&ring_free[slot], ph ^ 1u);
-                if (tc::elect_one()) {
-                    tc::mbar_arrive_expect_tx(&ring_full[slot], kTileBytes);
-                    tc::tma_load_3d(sR + slot * kTileBytes, &p.tmV, &ring_full[slot], (half_idx * VS + j) * 64, g * kKVTile, nb);
-                }
-                __syncwarp();
-                if (++slot == R) { slot = 0; ph ^= 1u; }
-            }
-        };
-        load_k(0);
-        if (G > 1) load_k(1);
-        for (int g = 0; g < G; ++g) {
-            load_v(g);
-            if (g + 2 < G) load_k(g + 2);
         }
+        __syncwarp();
     } else if (warp == 4) {
-        // ------------------------------------------------------------------------------ MMA issuer
-        const uint32_t sQ_a = tc::smem_u32(sQ), sR_a = tc::smem_u32(sR);
-        int slot = 0;
-        uint32_t ph = 0;
-        // S(g) = Q K(g)^T into buffer g & 1: KQ k-blocks x 4 MMAs (K = 16 each)
-        auto issue_s = [&](int g) {
-            const int nk = block_nk(g);
-            const uint32_t idesc = tc::umma_idesc_f16(128, (uint32_t)nk, 0, 0);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(g & 1) * 128u;
-            for (int kb = 0; kb < KQ; ++kb) {
-                tc::mbar_wait(&ring_full[slot], ph);
-                tc::tc_fence_after();
-                if (tc::elect_one()) {
-                    const uint64_t qd = tc::umma_desc_sw128(sQ_a + (uint32_t)kb * kTileBytes);
-                    const uint64_t kd = tc::umma_desc_sw128(sR_a + (uint32_t)slot * kTileBytes);
+        // ------------------------------------------------------------------------------ issuer of the S MMAs (one elected lane)
+        if (tc::elect_one()) {
+            const uint32_t sQ_a = tc::smem_u32(sQ), sK_a = tc::smem_u32(sKr);
+            const uint64_t qd0 = tc::umma_desc_sw128(sQ_a), kd0 = tc::umma_desc_sw128(sK_a);
+            int slot = 0;
+            uint32_t ph = 0;
+            tc::mbar_wait(bar_q, 0);
+            for (int g = 0; g < G; ++g) {
+                if (g >= 2) {
+                    tc::mbar_wait(&o_done[g & 1], (uint32_t)(((g - 2) >> 1) & 1));   // PV(g-2) retired: its P buffer may be overwritten
+                    tc::tc_fence_after();
+                }
+                // S(g) = Q K(g)^T into buffer g & 1: KQ k-blocks x 4 MMAs (K = 16 each)
+                const uint32_t idesc = tc::umma_idesc_f16(128, (uint32_t)block_nk(g), 0, 0);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(g & 1) * 128u;
+                for (int kb = 0; kb < KQ; ++kb) {
+                    tc::mbar_wait(&k_full[slot], ph);
+                    tc::tc_fence_after();
+                    const uint64_t qd = qd0 + (uint64_t)(kb * (kTileBytes >> 4));
+                    const uint64_t kd = kd0 + (uint64_t)(slot * (kTileBytes >> 4));
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         tc::umma_f16(d_tmem, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-                    tc::umma_commit(&ring_free[slot]);
-                    if (kb == KQ - 1) tc::umma_commit(&s_full[g & 1]);
+                    tc::umma_commit(&k_free[slot]);
+                    if (++slot == RK) { slot = 0; ph ^= 1u; }
                 }
-                __syncwarp();
-                if (++slot == R) { slot = 0; ph ^= 1u; }
+                tc::umma_commit(&s_full[g & 1]);
             }
-        };
-        // O[:, 64 j : 64 j + 64] += P(g) V(g)[:, sub-tile j]   (P from tensor memory, V sub-tile MN-major)
-        auto issue_pv = [&](int g) {
-            const int nk = block_nk(g);
-            const uint32_t idesc_o = tc::umma_idesc_f16(128, 64, 0, 1);
-            const uint32_t p_tmem = tmem_base + (uint32_t)(g & 1) * 128u;
-            for (int j = 0; j < VS; ++j) {
-                tc::mbar_wait(&ring_full[slot], ph);
-                tc::tc_fence_after();
-                if (tc::elect_one()) {
-                    const uint64_t vd = tc::umma_desc_sw128(sR_a + (uint32_t)slot * kTileBytes);
-                    for (int t = 0; t < nk / 16; ++t)
-                        tc::umma_f16_ts(tmem_base + kTmemO + (uint32_t)(j * 64), p_tmem + (uint32_t)(t * 8), vd + (uint64_t)(t * 128),
-                                        idesc_o, (g != 0 || t != 0) ? 1u : 0u);
-                    tc::umma_commit(&ring_free[slot]);
-                    if (j == VS - 1) tc::umma_commit(o_done);
-                }
-                __syncwarp();
-                if (++slot == R) { slot = 0; ph ^= 1u; }
-            }
-        };
-        tc::mbar_wait(bar_q, 0);
-        tc::tc_fence_after();
-        issue_s(0);
-        if (G > 1) issue_s(1);
-        for (int g = 0; g < G; ++g) {
-            tc::mbar_wait(&p_ready[g & 1], (uint32_t)((g >> 1) & 1));
-            tc::tc_fence_after();
-            issue_pv(g);
-            if (g + 2 < G) issue_s(g + 2);     // overwrites P(g)'s buffer: issued behind PV(g), executes behind it
         }
+        __syncwarp();
+    } else if (warp == 6) {
+        // ------------------------------------------------------------------------------ issuer of the PV MMAs (one elected lane)
+        // O[:, 64 j : 64 j + 64] += P(g) V(g)[:, sub-tile j]   (P from tensor memory, V sub-tile MN-major)
+        if (tc::elect_one()) {
+            const uint64_t vd0 = tc::umma_desc_sw128(tc::smem_u32(sVr));
+            const uint32_t idesc_o = tc::umma_idesc_f16(128, 64, 0, 1);
+            int slot = 0;
+            uint32_t ph = 0;
+            for (int g = 0; g < G; ++g) {
+                const int nk = block_nk(g);
+                const uint32_t p_tmem = tmem_base + (uint32_t)(g & 1) * 128u;
+                tc::mbar_wait(&p_ready[g & 1], (uint32_t)((g >> 1) & 1));
+                tc::tc_fence_after();
+                for (int j = 0; j < VS; ++j) {
+                    tc::mbar_wait(&v_full[slot], ph);
+                    tc::tc_fence_after();
+                    const uint64_t vd = vd0 + (uint64_t)(slot * (kTileBytes >> 4));
+                    const uint32_t d_tmem = tmem_base + kTmemO + (uint32_t)(j * 64);
+                    if (nk == kKVTile) {
+#pragma unroll
+                        for (int t = 0; t < kKVTile / 16; ++t)
+                            tc::umma_f16_ts(d_tmem, p_tmem + (uint32_t)(t * 8), vd + (uint64_t)(t * 128), idesc_o, (g != 0 || t != 0) ? 1u : 0u);
+                    } else {
+                        for (int t = 0; t < nk / 16; ++t)
+                            tc::umma_f16_ts(d_tmem, p_tmem + (uint32_t)(t * 8), vd + (uint64_t)(t * 128), idesc_o, (g != 0 || t != 0) ? 1u : 0u);
+                    }
+                    tc::umma_commit(&v_free[slot]);
+                    if (++slot == RV) { slot = 0; ph ^= 1u; }
+                }
+                tc::umma_commit(&o_done[g & 1]);
+            }
+        }
+        __syncwarp();
     } else {
         // ------------------------------------------------------------------------------ softmax (one row per thread)
         const int row = tid;                                  // 0..127
@@ -260,12 +275,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn_wide_kernel(const __grid_
             const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
             const bool grow = (m_new - m_run) * c > kRescaleThreshold;    // first block: +inf -> true
             const float m_use = grow ? m_new : m_run;
-            // o_done completes one phase per key block and is awaited by PARITY, so every block's phase must be consumed
-            // exactly once and in order (a wait that lags two phases behind returns at once): before the exponentials when
-            // O has to be rescaled, after them otherwise (the PV MMA of the previous block then retires underneath).
+            // o_done[] is awaited by PARITY: every block's phase is consumed exactly once and in order (a wait that lags two
+            // phases behind would return at once) — before the exponentials when O has to be rescaled, after them
+            // otherwise (the PV MMA of the previous block then retires underneath).
             const bool rescale = g > 0 && __any_sync(0xffffffffu, grow);
             if (rescale) {
-                tc::mbar_wait(o_done, (uint32_t)((g - 1) & 1));
+                tc::mbar_wait(&o_done[(g - 1) & 1], (uint32_t)(((g - 1) >> 1) & 1));
                 tc::tc_fence_after();
                 const float alpha = ex2((m_run - m_use) * c);
                 l_run *= alpha;
@@ -294,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn_wide_kernel(const __grid_
                 else sum_a = add2(sum_a, pack2(e0, e1));
                 pk[j] = pack_h2(e0, e1);
             }
-            if (g > 0 && !rescale) tc::mbar_wait(o_done, (uint32_t)((g - 1) & 1));
+            if (g > 0 && !rescale) tc::mbar_wait(&o_done[(g - 1) & 1], (uint32_t)(((g - 1) >> 1) & 1));
             // P overwrites the first 64 columns of this block's S buffer (every thread has its whole S row in registers)
             tc::tmem_st32(tmem_s, &pk[0]);
             tc::tmem_st32(tmem_s + 32, &pk[32]);
@@ -307,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn_wide_kernel(const __grid_
             l_run += (a0 + a1) + (b0 + b1);
         }
         // ---- epilogue: O / l -> fp16 -> global (this CTA's channel slice)
-        tc::mbar_wait(o_done, (uint32_t)((G - 1) & 1));
+        tc::mbar_wait(&o_done[(G - 1) & 1], (uint32_t)(((G - 1) >> 1) & 1));
         tc::tc_fence_after();
         const float inv_l = 1.0f / l_run;
         const int qrow = q0 + row;
@@ -381,11 +396,13 @@ extern "C" int tc_attention_wide(const void* q, const void* k, const void* v, lo
     p.ldo = ldo;
     p.scale_log2 = scale * 1.4426950408889634f;
     const int budget = 227 * 1024 - 1024 - 1024;          // alignment slack, barriers
-    int ring = (budget - p.kq * kTileBytes) / kTileBytes;
-    if (ring > 12) ring = 12;
-    TC_CHECK_ARG(ring >= 3, "tc_attention_wide: not enough shared memory for the K/V ring");
-    p.ring = ring;
-    const size_t smem_bytes = (size_t)(p.kq + ring) * kTileBytes + 2048;
+    int slots = (budget - p.kq * kTileBytes) / kTileBytes;
+    if (slots > 12) slots = 12;
+    TC_CHECK_ARG(slots >= 4, "tc_attention_wide: not enough shared memory for the K and V rings");
+    p.rv = slots / 3 < 2 ? 2 : slots / 3;                 // a third of the slots (>= 2) stream V, the rest K
+    if (p.rv > p.vs) p.rv = p.vs < 2 ? 2 : p.vs;
+    p.rk = slots - p.rv;
+    const size_t smem_bytes = (size_t)(p.kq + slots) * kTileBytes + 2048;
     static bool attr_set = false;
     if (!attr_set) {
         int rc = check_cuda(cudaFuncSetAttribute(tc_attn_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
