@@ -88,7 +88,8 @@ struct alignas(64) GemmKParams {
     FastDiv fd_ks, fd_kc;           // ksplit, kc_per_tap
     float* ws_partial;              // [total tiles][ksplit][128 rows][BN] floats
     unsigned int* ws_ticket;        // [total tiles], zero between launches (the last slice resets it)
-    int stage_bufs;                 // 1 or 2 output staging boxes (2: short-K launches, whose epilogue is the bottleneck)
+    int stage_bufs;                 // output staging boxes per warp / column group (1; 2 in rotation; or one per chunk: batch_store)
+    int batch_store;                // short-K launches: all chunks of a tile are staged, then stored in one burst
     int n_cols;
     int stages;
     uint32_t a_bytes;  // bytes delivered per A box
@@ -485,6 +486,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     tc::tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
                     TC_TRACE(2, ti)
+                    int pend = -1;
+                    (void)pend;
                     for (int kb = 0; kb < n_main; ++kb) {
                         tc::mbar_wait(&full_bar[stage], phase);
                         tc::tc_fence_after();
@@ -499,7 +502,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                             else
                                 tc::umma_f16(d_tmem, mk(a_lo + 2u * k, a_hi), mk(b_lo + 2u * k, b_hi), idesc, (kb | k) != 0 ? 1u : 0u);
                         }
+#if defined(TC_GEMM_COMMIT2)
+                        // (experiment) release operand stages two k-blocks at a time: two back-to-back commits per pair
+                        if ((kb & 1) || kb == n_main - 1) {
+                            if (pend >= 0) { if constexpr (kPair) tc::umma_commit_pair(&empty_bar[pend]); else tc::umma_commit(&empty_bar[pend]); }
+                            if constexpr (kPair) tc::umma_commit_pair(&empty_bar[stage]); else tc::umma_commit(&empty_bar[stage]);
+                            pend = -1;
+                        } else {
+                            pend = stage;
+                        }
+#else
                         if constexpr (kPair) tc::umma_commit_pair(&empty_bar[stage]); else tc::umma_commit(&empty_bar[stage]);
+#endif
                         if (++stage == S) {
                             stage = 0;
                             phase ^= 1u;
@@ -944,6 +958,31 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                         }
                     }
                     if (threadIdx.x == 64 && jc == 0) { TC_TRACE(9, ti) }      // math done
+                    if (p.batch_store) {
+                        // ---- short-K launches (epilogue-bound): every chunk of the tile has its own staging box, so the box-free
+                        // wait, the proxy fence, the barrier and the store issue — ~1000 cycles of serial latency per chunk in the
+                        // in-kernel timeline (profiles/r02_gemm_trace_k320.txt) — are paid once per tile, after the chunk loop
+                        if (jc == 0) {
+                            if (store_warp) {
+                                if (tc::elect_one()) tc::bulk_wait_group_read<0>();     // the previous tile's stores have read every box
+                            }
+                            if (warp_box) __syncwarp();
+                            else if (cg == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+                            else asm volatile("bar.sync 3, 128;" ::: "memory");
+                            if (threadIdx.x == 64) { TC_TRACE(10, ti) }     // staging boxes free
+                        }
+                        const uint32_t stg_row_b = stg_row + (uint32_t)jc * 16384u;
+                        if (!(dbg & 16))
+#pragma unroll
+                        for (int hh = 0; hh < 4; ++hh) {
+                            const uint32_t dst = stg_row_b + ((((uint32_t)hh) ^ stg_swz) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * hh]),
+                                         "r"(pk[4 * hh + 1]), "r"(pk[4 * hh + 2]), "r"(pk[4 * hh + 3])
+                                         : "memory");
+                        }
+                        if (threadIdx.x == 64 && jc == 0) { TC_TRACE(11, ti) }     // staged
+                        continue;
+                    }
                     // two staging boxes in rotation: only the store issued two chunks ago must have drained this one
                     const uint32_t buf = n_stores & (uint32_t)(p.stage_bufs - 1);
                     uint8_t* stg_b = stg + buf * 16384u;
@@ -986,6 +1025,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                         }
                     }
                     if (threadIdx.x == 64 && jc == 0) { TC_TRACE(13, ti) }     // store issued
+                }
+                if (p.batch_store) {
+                    // one proxy fence, one barrier, then the whole tile's stores from one elected lane and ONE commit
+                    if (!(dbg & 8)) tc::fence_proxy_async_smem();
+                    if (warp_box) __syncwarp();
+                    else if (cg == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+                    else asm volatile("bar.sync 3, 128;" ::: "memory");
+                    if (threadIdx.x == 64) { TC_TRACE(12, ti) }
+                    if (store_warp && !(dbg & 1) && (!warp_box || warp_rows_in_tile)) {
+                        if (tc::elect_one()) {
+                            for (int jc = 0; jc < 4; ++jc) {
+                                const int c = (cg + 2 * jc) * 32;
+                                if (c >= width) break;
+                                if (warp_box) tc::tma_store_4d(stg + jc * 16384, &p.tmOw, nt * width + c, x0 + wx, y0 + wy, n0 + wn);
+                                else tc::tma_store_4d(stg + jc * 16384, &p.tmO, nt * width + c, x0, y0, n0);
+                            }
+                            tc::bulk_commit_group();
+                        }
+                    }
+                    if (threadIdx.x == 64) { TC_TRACE(13, ti) }     // stores issued
                 }
                 float rs_sum = 0.f, rs_sq = 0.f;
                 if (kEpi == 0 && p.row_stats) {
@@ -1445,6 +1504,15 @@ extern "C" int tc_conv_gemm(const TcConvGemm* d, void* stream_v) {
     // a second staging box pays off where the epilogue bounds the tile time (short K loops); long K loops would rather
     // have the 16 KiB as operand pipeline depth (conv 320->320 lost 10 % when it went from 5 to 4 stages)
     p.stage_bufs = (p.tma_store && d->taps * (d->a_C / kBlockK) <= 12) ? 2 : 1;
+    {
+        static const char* bs_env = getenv("TC_GEMM_BATCH_STORE");   // "0" disables (A/B testing)
+        const int width = geglu ? BN / 2 : BN;
+        const int chunks_per_group = (width / 32 + 1) / 2;
+        if (p.stage_bufs == 2 && p.ksplit == 1 && chunks_per_group <= 4 && !(bs_env && bs_env[0] == '0')) {
+            p.batch_store = 1;
+            p.stage_bufs = chunks_per_group;
+        }
+    }
     // alignment slack, barriers, epilogue vectors, store staging, identity tile, row-statistics hand-over
     const int kFixedSmem = 1024 + 512 + 4096 + 1024 + 16384 * p.stage_bufs + 8192 + 2048;
     const int smem_budget = 227 * 1024 - kFixedSmem;
