@@ -77,6 +77,15 @@ def bench_attn(B, L, heads, Lk=None):
     return dict(kind="attention", shape=[B, L, Lk, heads], ms=ms, tflops=4.0 * B * heads * L * Lk * 64 / ms / 1e9)
 
 
+def bench_attn_wide(N, L, D):
+    """fused single-head attention of the VAE mid block (head dim D)"""
+    qkv = torch.randn(N, L, 3 * D, device=DEV).half()
+    out = torch.empty(N, L, D, device=DEV, dtype=torch.float16)
+    fn = lambda: ops.attention_wide(qkv, out, batches=N, L=L, D=D, scale=D ** -0.5, ld=3 * D, ldo=D, k_offset=D, v_offset=2 * D)
+    ms = timeit(fn)
+    return dict(kind="attention_wide", shape=[N, L, D], ms=ms, tflops=4.0 * N * L * L * D / ms / 1e9)
+
+
 def bench_gn(frames, fps, hw, C):
     x = torch.randn(frames, hw, C, device=DEV).half()
     y = torch.empty_like(x)

@@ -6,6 +6,8 @@
 //
 // Algorithmic bytes: GroupNorm = 2 reads + 1 write of the activation (statistics pass + apply pass; the second
 // read hits L2 for UNet-sized tensors); LayerNorm = 1 read + 1 write.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 #include "tc_host.h"
 
@@ -174,6 +176,138 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, long long ldx, __h
     }
 }
 
+// ---- single-pass GroupNorm for small / medium tensors: one CTA (or a cluster of 2-8 CTAs) per (stat group, norm group) -----
+// The two-kernel path costs ~5 us of launch / tail per kernel plus two reads of the tensor: 12-23 us (back to back) for the
+// 3-13 MB activations of UNet levels 2 and 3 (77 of the 166 GroupNorms of a forward); this kernel 8-18 us.  Here the unit's elements — `cpg` contiguous
+// channels of every pixel of the stat group — are loaded ONCE into registers (kVec-byte vectors, at most kMaxV per thread),
+// reduced (warp shuffles -> shared memory -> fixed-order sum; across a cluster through distributed shared memory, summed in
+// rank order: deterministic), normalised (+SiLU) in registers and stored.  One read, one write, one launch.
+__device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t rank) {
+    float v;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %1, %2;\n\t"
+        "ld.shared::cluster.f32 %0, [ra];\n\t"
+        "}\n"
+        : "=f"(v)
+        : "r"(tc::smem_u32(local_ptr)), "r"(rank)
+        : "memory");
+    return v;
+}
+
+template <int kMaxV>
+__global__ void __launch_bounds__(640, 1) gn_fused_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           long long pixels_per_stat, int C, int G, float eps, int silu, int csize) {
+    tc::pdl_wait();   // no early launch_dependents (see gn_stats_kernel)
+    __shared__ float s_part[2][32];      // per-warp partial {sum, sumsq}
+    __shared__ float s_cta[2];           // this CTA's {sum, sumsq}: read by the cluster peers
+    __shared__ float s_stat[2];          // {mean, rstd}
+    const int cpg = C / G;
+    const int vpp = cpg >> 3;                         // 16-byte vectors per pixel of this norm group
+    const int unit = (int)blockIdx.x / csize;         // (stat group, norm group)
+    const uint32_t rank = csize > 1 ? tc::cluster_ctarank() : 0u;
+    const int s = unit / G, g = unit - s * G;
+    const int T = (int)blockDim.x;                    // a multiple of vpp: thread t always owns channel vector t % vpp
+    const int k = (int)threadIdx.x % vpp;
+    const long long total_v = pixels_per_stat * vpp;
+    const long long per_cta = (total_v + csize - 1) / csize;
+    long long v_begin = (long long)rank * per_cta;
+    v_begin -= v_begin % vpp;                         // whole pixels per CTA (keeps t % vpp == channel vector)
+    long long v_end = (long long)(rank + 1) * per_cta;
+    v_end -= v_end % vpp;
+    if ((int)rank == csize - 1) v_end = total_v;
+    const __half* xb = x + (long long)s * pixels_per_stat * ldx + (long long)g * cpg + (long long)k * 8;
+    __half* yb = y + (long long)s * pixels_per_stat * ldy + (long long)g * cpg + (long long)k * 8;
+
+    uint4 u[kMaxV];
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) {
+        const long long v = v_begin + threadIdx.x + (long long)i * T;
+        if (v < v_end) u[i] = *reinterpret_cast<const uint4*>(xb + (v / vpp) * ldx);
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) {
+        const long long v = v_begin + threadIdx.x + (long long)i * T;
+        if (v < v_end) {
+            float f[8];
+            unpack8(u[i], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                sum += f[j];
+                sq += f[j] * f[j];
+            }
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = T >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (lane == 0) {
+        s_part[0][warp] = sum;
+        s_part[1][warp] = sq;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < nwarps; ++w) {
+            a += s_part[0][w];
+            b += s_part[1][w];
+        }
+        s_cta[0] = a;
+        s_cta[1] = b;
+    }
+    if (csize > 1) tc::cluster_sync_all(); else __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        if (csize > 1) {
+            for (int r = 0; r < csize; ++r) {                // rank order: every CTA of the cluster computes the same bits
+                a += (double)ld_dsmem_f32(&s_cta[0], (uint32_t)r);
+                b += (double)ld_dsmem_f32(&s_cta[1], (uint32_t)r);
+            }
+        } else {
+            a = s_cta[0];
+            b = s_cta[1];
+        }
+        const double cnt = (double)pixels_per_stat * (double)cpg;
+        const double mean = a / cnt;
+        double var = b / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_stat[0] = (float)mean;
+        s_stat[1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const float mean = s_stat[0], rstd = s_stat[1];
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = g * cpg + k * 8 + j;
+        const float a = rstd * gamma[c];
+        sc[j] = a;
+        sh[j] = beta[c] - mean * a;
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) {
+        const long long v = v_begin + threadIdx.x + (long long)i * T;
+        if (v < v_end) {
+            float f[8];
+            unpack8(u[i], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float t = f[j] * sc[j] + sh[j];
+                if (silu) t = tc::silu_f(t);
+                f[j] = t;
+            }
+            *reinterpret_cast<uint4*>(yb + (v / vpp) * ldy) = pack8(f);
+        }
+    }
+    if (csize > 1) tc::cluster_sync_all();     // peers may still be reading this CTA's s_cta
+}
+
 // ---- LayerNorm: one warp per row, row kept in registers ------------------------------------------------
 template <int kMaxVec>
 __global__ void layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
@@ -308,6 +442,41 @@ extern "C" int tc_groupnorm(const void* x, long long ldx, void* y, long long ldy
     TC_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0, "tc_groupnorm: strides must be multiples of 8");
     const int n_stat = frames / frames_per_stat;
     const long long pps = (long long)frames_per_stat * hw;
+    {
+        // single-pass path: (C / G) % 8 == 0 (16-byte vectors per norm group) and the unit fits the registers of <= 8 CTAs
+        static const char* fused_env = getenv("TC_GN_FUSED");     // "0" disables (A/B testing)
+        const int cpg = C / G;
+        constexpr int kMaxV = 8;
+        // (large tensors stay on the streaming two-kernel path: 5+ TB/s there, and a unit's 16-80 bytes per pixel row
+        // would be a poor access pattern at hundreds of megabytes)
+        if (cpg % 8 == 0 && (long long)frames * hw * C * 2 <= (16LL << 20) && !(fused_env && fused_env[0] == '0')) {
+            const int vpp = cpg / 8;
+            const long long total_v = pps * vpp;
+            int threads = (640 / (32 * vpp)) * (32 * vpp);            // multiple of 32 and of vpp, <= 640
+            if (32 % vpp == 0) threads = 640;
+            if (threads >= 32 && total_v <= 8LL * threads * kMaxV) {
+                int csize = 1;
+                while ((long long)csize * threads * kMaxV < total_v + (long long)csize * (vpp + 1)) ++csize;   // whole pixels per CTA
+                // (26 MB tensors in 512 one-per-SM CTAs = 3.5 waves measured 43 us against 26 us on the two-kernel path)
+                if (csize <= 8 && (long long)n_stat * G * csize <= 2LL * sm_count()) {
+                    // small units: shrink the block to what the unit needs (keeps more units resident per SM)
+                    if (csize == 1) {
+                        const int step = (32 % vpp == 0) ? 32 : 32 * vpp;
+                        const long long need = (total_v + kMaxV / 2 - 1) / (kMaxV / 2);      // aim at <= 4 vectors per thread
+                        int t2 = (int)((need + step - 1) / step) * step;
+                        if (t2 < step) t2 = step;
+                        if (t2 < threads) threads = t2;
+                    }
+                    tc_host::launch(gn_fused_kernel<kMaxV>, dim3((unsigned)(n_stat * G * csize)), dim3(threads), 0, stream, csize,
+                                    reinterpret_cast<const __half*>(x), ldx, reinterpret_cast<__half*>(y), ldy, gamma, beta, pps, C, G,
+                                    eps, silu, csize);
+                    count_launch();
+                    TC_CHECK_LAUNCH("gn_fused_kernel");
+                    return TC_OK;
+                }
+            }
+        }
+    }
     const int V = C / 8;
     int k = 512 / V;
     if (k < 1) k = 1;
