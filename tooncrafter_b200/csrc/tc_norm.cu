@@ -458,11 +458,14 @@ extern "C" int tc_groupnorm(const void* x, long long ldx, void* y, long long ldy
                 int csize = 1;
                 while ((long long)csize * threads * kMaxV < total_v + (long long)csize * (vpp + 1)) ++csize;   // whole pixels per CTA
                 // (26 MB tensors in 512 one-per-SM CTAs = 3.5 waves measured 43 us against 26 us on the two-kernel path)
-                if (csize <= 8 && (long long)n_stat * G * csize <= 2LL * sm_count()) {
-                    // small units: shrink the block to what the unit needs (keeps more units resident per SM)
+                const long long n_units = (long long)n_stat * G;
+                if (csize <= 8 && (csize == 1 || n_units * csize <= 2LL * sm_count())) {
+                    // small units: shrink the block to what the unit needs (several units resident per SM); with many units
+                    // (per-frame statistics: 1024 of them) fewer, fuller threads keep the grid near one wave
                     if (csize == 1) {
                         const int step = (32 % vpp == 0) ? 32 : 32 * vpp;
-                        const long long need = (total_v + kMaxV / 2 - 1) / (kMaxV / 2);      // aim at <= 4 vectors per thread
+                        const int per_thread = n_units >= 4LL * sm_count() ? kMaxV : kMaxV / 2;
+                        const long long need = (total_v + per_thread - 1) / per_thread;
                         int t2 = (int)((need + step - 1) / step) * step;
                         if (t2 < step) t2 = step;
                         if (t2 < threads) threads = t2;
