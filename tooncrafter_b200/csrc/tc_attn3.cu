@@ -495,6 +495,7 @@ __global__ void __launch_bounds__(kXsThreads, 4) tc_attn_xs_kernel(const AttnXsP
     tc::pdl_wait();   // no early launch_dependents (see temporal_attn_mma_kernel)
     __shared__ __align__(128) uint8_t sK[kXsMaxNT * 8 * 128];   // [key][64 halfs], 16-byte chunks XOR-swizzled by key & 7
     __shared__ __align__(128) uint8_t sV[kXsMaxNT * 8 * 128];
+    __shared__ __align__(128) uint8_t sQO[kXsThreads / 32][16 * 128];   // per warp: 16 query rows x 64 halfs (Q in, then O out), 16-byte chunks XOR-swizzled by row & 7
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g8 = lane >> 2, t4 = lane & 3;
     const int head = blockIdx.y, qb = blockIdx.z;
@@ -536,32 +537,44 @@ __global__ void __launch_bounds__(kXsThreads, 4) tc_attn_xs_kernel(const AttnXsP
     const float c = p.scale_log2;
     const int n_groups = (p.Lq + 15) >> 4;
 
-    // Q fragments (A operand, rows g8 and g8 + 8 of a 16-query group) straight from global memory; the NEXT group's are
-    // requested while this group's softmax / PV run (a warp's first HMMA sat on this load: 12 % of the samples)
-    auto load_q = [&](int grp, uint32_t (&dst)[4][4]) {
-        const int r0 = grp * 16 + g8, r1 = r0 + 8;
-        const bool ok0 = grp < n_groups && r0 < p.Lq, ok1 = grp < n_groups && r1 < p.Lq;
-        const __half* q0p = p.q + ((long long)qb * p.Lq + r0) * p.ldq + head * 64;
-        const __half* q1p = p.q + ((long long)qb * p.Lq + r1) * p.ldq + head * 64;
+    // Q rows of a 16-query group come in as 16-byte vectors (8 lanes cover the 128 bytes of a row: every sector fully used;
+    // the 4-byte fragment loads of the first version used half of every 32-byte sector, and so did its stores), pass through
+    // this warp's staging tile and become A fragments by ldmatrix.  The NEXT group's vectors are requested while this
+    // group's softmax / PV run (a warp's first HMMA sat on this load: 12 % of the samples).
+    const uint32_t sQO_a = tc::smem_u32(&sQO[warp][0]);
+    const int st_row = lane >> 3, st_chunk = lane & 7;                 // staging: lane <-> (row st_row + 4 i, 16-byte chunk)
+    auto load_q = [&](int grp, uint4 (&dst)[4]) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            const int col = 16 * ks + 2 * t4;
-            dst[ks][0] = ok0 ? *reinterpret_cast<const uint32_t*>(q0p + col) : 0u;
-            dst[ks][1] = ok1 ? *reinterpret_cast<const uint32_t*>(q1p + col) : 0u;
-            dst[ks][2] = ok0 ? *reinterpret_cast<const uint32_t*>(q0p + col + 8) : 0u;
-            dst[ks][3] = ok1 ? *reinterpret_cast<const uint32_t*>(q1p + col + 8) : 0u;
+        for (int i = 0; i < 4; ++i) {
+            const int r = grp * 16 + st_row + 4 * i;
+            dst[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (grp < n_groups && r < p.Lq)
+                dst[i] = *reinterpret_cast<const uint4*>(p.q + ((long long)qb * p.Lq + r) * p.ldq + head * 64 + st_chunk * 8);
         }
     };
-    uint32_t qn[4][4];
+    uint4 qn[4];
     load_q((int)blockIdx.x * 4 + warp, qn);
     for (int grp = (int)blockIdx.x * 4 + warp; grp < n_groups; grp += (int)gridDim.x * 4) {
         const int r0 = grp * 16 + g8, r1 = r0 + 8;
-        const bool ok0 = r0 < p.Lq, ok1 = r1 < p.Lq;
+        (void)r0; (void)r1;
         uint32_t qa[4][4];
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
+        for (int i = 0; i < 4; ++i) {
+            const int row = st_row + 4 * i;
+            const uint32_t a = sQO_a + (uint32_t)(row * 128 + ((st_chunk ^ (row & 7)) << 4));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(qn[i].x), "r"(qn[i].y), "r"(qn[i].z), "r"(qn[i].w) : "memory");
+        }
+        __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) qa[ks][i] = qn[ks][i];
+        for (int ks = 0; ks < 4; ++ks) {
+            // matrices: (rows 0-7, k 0-7), (rows 8-15, k 0-7), (rows 0-7, k 8-15), (rows 8-15, k 8-15) of k-step ks
+            const int row = ((lane >> 3) & 1) * 8 + (lane & 7);
+            const int chunk = 2 * ks + (lane >> 4);
+            const uint32_t a = sQO_a + (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(qa[ks][0]), "=r"(qa[ks][1]), "=r"(qa[ks][2]), "=r"(qa[ks][3])
+                         : "r"(a));
+        }
         // ---- S = Q K^T: per n-tile two ldmatrix.x4 (d chunks 0-31, 32-63 of keys 8nt..8nt+7)
         float sacc[kXsMaxNT][4];
 #pragma unroll
@@ -680,13 +693,26 @@ __global__ void __launch_bounds__(kXsThreads, 4) tc_attn_xs_kernel(const AttnXsP
                 }
             }
         }
-        __half* o0p = p.out + ((long long)qb * p.Lq + r0) * p.ldo + head * 64;
-        __half* o1p = p.out + ((long long)qb * p.Lq + r1) * p.ldo + head * 64;
+        // ---- O: fragments -> staging tile (the Q fragments are long consumed) -> 16-byte row-contiguous global stores
+        __syncwarp();
 #pragma unroll
         for (int nd = 0; nd < 8; ++nd) {
-            if (ok0) *reinterpret_cast<uint32_t*>(o0p + 8 * nd + 2 * t4) = pack_h2(oacc[nd][0], oacc[nd][1]);
-            if (ok1) *reinterpret_cast<uint32_t*>(o1p + 8 * nd + 2 * t4) = pack_h2(oacc[nd][2], oacc[nd][3]);
+            const uint32_t a0 = sQO_a + (uint32_t)(g8 * 128 + ((nd ^ (g8 & 7)) << 4) + t4 * 4);
+            const uint32_t a1 = sQO_a + (uint32_t)((g8 + 8) * 128 + ((nd ^ (g8 & 7)) << 4) + t4 * 4);      // (g8 + 8) & 7 == g8 & 7
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a0), "r"(pack_h2(oacc[nd][0], oacc[nd][1])) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a1), "r"(pack_h2(oacc[nd][2], oacc[nd][3])) : "memory");
         }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = st_row + 4 * i;
+            const int r = grp * 16 + row;
+            const uint32_t a = sQO_a + (uint32_t)(row * 128 + ((st_chunk ^ (row & 7)) << 4));
+            uint4 u;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(a) : "memory");
+            if (r < p.Lq) *reinterpret_cast<uint4*>(p.out + ((long long)qb * p.Lq + r) * p.ldo + head * 64 + st_chunk * 8) = u;
+        }
+        __syncwarp();
     }
 }
 
@@ -763,7 +789,7 @@ int tc_attention_v3(const TcAttention* d, int poly_of_8, cudaStream_t stream) {
 int tc_attention_xs(const TcAttention* d, cudaStream_t stream) {
     const int nk0 = (d->Lk[0] + 15) & ~15, nk1 = d->n_seg > 1 ? ((d->Lk[1] + 15) & ~15) : 0;
     if (nk0 + nk1 > 8 * kXsMaxNT) return TC_ERR_INVALID;
-    if ((d->ldq % 8) || (d->ldo % 2)) return TC_ERR_INVALID;
+    if ((d->ldq % 8) || (d->ldo % 8) || ((reinterpret_cast<uintptr_t>(d->q) | reinterpret_cast<uintptr_t>(d->out)) & 15)) return TC_ERR_INVALID;   // 16-byte row vectors
     AttnXsParams p;
     memset(&p, 0, sizeof(p));
     p.q = reinterpret_cast<const __half*>(d->q);
