@@ -524,6 +524,17 @@ def test_softmax_rows(ops):
     _close(s, ref, "softmax rows", rel=2e-3, abs_=1e-5)
 
 
+def test_ncthw_to_cl_wide_channels(ops):
+    """Tiled transpose used for the decoder's reference feature maps (C % 64 == 0): ragged pixel count, channel slice."""
+    B, Cc, T, H, W, Cpad, coff = 2, 128, 3, 7, 9, 256, 64
+    x = _rand(B, Cc, T, H, W, seed=131)
+    y = torch.zeros(B, T, H, W, Cpad, dtype=torch.float16, device=DEV)
+    ops.ncthw_to_cl(x, y, B=B, C_=Cc, T=T, H=H, W=W, Cpad=Cpad, coff=coff, scale=0.25)
+    ref = (x * 0.25).permute(0, 2, 3, 4, 1).half()
+    assert torch.equal(y[..., coff:coff + Cc], ref), "tiled ncthw_to_cl differs from the reference layout change"
+    assert (y[..., :coff] == 0).all() and (y[..., coff + Cc:] == 0).all(), "channels outside the slice were touched"
+
+
 def test_layout_and_elementwise(ops):
     B, Cc, T, H, W = 2, 4, 3, 6, 8
     x = _rand(B, Cc, T, H, W, seed=91)

@@ -1,5 +1,7 @@
 // tooncrafter_b200 — data-movement / elementwise kernels, tiny linears and the fused DDIM update (HBM-bound).
 // Reference sites are listed per entry point in include/tooncrafter_b200.h.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 #include "tc_host.h"
 
@@ -20,6 +22,39 @@ __global__ void ncthw_to_cl_kernel(const float* __restrict__ x, __half* __restri
         const float* src = x + b * C * thw + r;
         __half* dst = y + i * Cpad + coff;
         for (int c = 0; c < C; ++c) dst[c] = __float2half_rn(src[(long long)c * thw] * scale);
+    }
+}
+
+// Tiled form for wide tensors (C % 64 == 0: the decoder's reference-frame feature maps, 128-512 channels): a 32-pixel x
+// 64-channel tile goes through shared memory, so the fp32 planes are read 128 bytes at a time AND the channels-last rows are
+// written as 16-byte vectors (the per-pixel loop above writes 2 bytes per thread per instruction: 460 GB/s, 1.7 ms of a
+// 47 ms decode, profiles/r02_vae_decode_launches.txt).  grid = (pixel tiles, channel tiles, B), 256 threads.
+__global__ void ncthw_to_cl_tiled_kernel(const float* __restrict__ x, __half* __restrict__ y, int C, long long thw, int Cpad,
+                                         int coff, float scale) {
+    tc::pdl_wait();
+    __shared__ float tile[64][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long r0 = (long long)blockIdx.x * 32;
+    const int c0 = (int)blockIdx.y * 64;
+    const long long b = blockIdx.z;
+    const float* src = x + (b * C + c0) * thw + r0 + lane;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = warp + 8 * k;
+        tile[c][lane] = (r0 + lane < thw) ? src[(long long)c * thw] * scale : 0.f;
+    }
+    __syncthreads();
+    const int p = threadIdx.x >> 3, chunk = threadIdx.x & 7;          // 32 pixels x 8 chunks of 8 channels
+    if (r0 + p < thw) {
+        __half2 h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(tile[chunk * 8 + 2 * j][p], tile[chunk * 8 + 2 * j + 1][p]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h[0]);
+        u.y = *reinterpret_cast<uint32_t*>(&h[1]);
+        u.z = *reinterpret_cast<uint32_t*>(&h[2]);
+        u.w = *reinterpret_cast<uint32_t*>(&h[3]);
+        *reinterpret_cast<uint4*>(y + (b * thw + r0 + p) * Cpad + coff + c0 + chunk * 8) = u;
     }
 }
 
@@ -341,6 +376,16 @@ extern "C" int tc_ncthw_to_cl(const float* x, void* y, int B, int C, int T, int 
     TC_CHECK_ARG(x && y && B > 0 && C > 0 && T > 0 && H > 0 && W > 0, "tc_ncthw_to_cl: bad arguments");
     TC_CHECK_ARG(coff >= 0 && coff + C <= Cpad, "tc_ncthw_to_cl: channel slice out of range");
     const long long npix = (long long)B * T * H * W;
+    const long long thw = (long long)T * H * W;
+    static const char* tiled_env = getenv("TC_NCTHW_TILED");   // "0" keeps the per-pixel kernel (A/B testing)
+    if (C % 64 == 0 && Cpad % 8 == 0 && coff % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && B <= 65535 &&
+        !(tiled_env && tiled_env[0] == '0')) {
+        tc_host::launch(ncthw_to_cl_tiled_kernel, dim3((unsigned)((thw + 31) / 32), (unsigned)(C / 64), (unsigned)B), dim3(256), 0, stream, 1, x,
+                        reinterpret_cast<__half*>(y), C, thw, Cpad, coff, scale);
+        count_launch();
+        TC_CHECK_LAUNCH("ncthw_to_cl_tiled_kernel");
+        return TC_OK;
+    }
     tc_host::launch(ncthw_to_cl_kernel, dim3(grid_for(npix, 256, 8 * sm_count())), dim3(256), 0, stream, 1, x, reinterpret_cast<__half*>(y), B,
                                                                                 C, T, H, W, Cpad, coff, scale);
     count_launch();
