@@ -43,8 +43,9 @@ def variants():
             yield f"v3 poly={p}/8", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY=str(p))
     yield "v3 p0", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY="0")
     yield "v3 p1", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY="1")
-    yield "v3 p0 token", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY="0", TC_ATTN_PP="1")
-    yield "v3 p0 stagger", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY="0", TC_ATTN_STAGGER="1200")
+    if os.environ.get("ATTN_AB_ALL") == "1":
+        yield "v3 p0 token", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY="0", TC_ATTN_PP="1")
+        yield "v3 p0 stagger", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY="0", TC_ATTN_STAGGER="1200")
 
 
 def set_env(e):

@@ -8,7 +8,8 @@
 //   * the row maximum uses 3-input max, scale / sum use packed f32x2 arithmetic, and a compile-time fraction of the
 //     exponentials runs on the FMA pipe (Cody-Waite range reduction + degree-3 polynomial) instead of MUFU: at
 //     head dim 64 the 16 MUFU lanes per SM cap an all-MUFU softmax at 50 % tensor-pipe utilisation.
-//   Two query tiles per CTA ping-pong through two softmax warpgroups (one query row per thread).
+//   Two query tiles per CTA run through two softmax warpgroups (one query row per thread), each tile with its own MMA-issuer
+//   warp (attn_issue_tile).
 //
 // Reference sites: lvdm/modules/attention.py:81-209 (spatial self-attention), lvdm/models/autoencoder_dualref.py:270-341
 // (dual-reference fusion attention).  Measured pipe rates behind the design: profiles/r02_pipe_rates.txt.

@@ -19,6 +19,9 @@
 //                                where the tile geometry allows, else one 128x32 box per column group).  Optional
 //                                per-row {sum, sumsq} of the outputs for the consumer's LayerNorm fold.  Odd widths
 //                                (n_cols % 32 != 0, e.g. the 4-channel output conv) take the direct-store variant.
+//                                Short-K launches (epilogue-bound) stage ALL chunks of a tile and issue their TMA stores in
+//                                one burst behind a single proxy fence / barrier / commit.
+//   The producer and the issuer are single-thread loops (one elected lane runs the whole loop, waits included).
 //   Three instantiations of the epilogue (plain / GEGLU / direct-store) x {single CTA, CTA pair}; tile shape and pairing
 //   come from choose_tiles() (waves x per-tile cost with the tensor rate and the ~52 B/clk/SM L2->SM ingest bound).
 //
@@ -273,7 +276,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     const int tn = fdiv(mt, p.fd_xy);                                          \
     const int ty = mtx_ - tn * p.tiles_y;
 
-#if !defined(TC_GEMM_ISSUE_LEGACY)
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         // ONE elected lane runs the whole loop, waits included (like the MMA issuer below).  A plain `if (lane == 0)` makes
@@ -355,99 +357,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             }
         }
         __syncwarp();
-#else
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        // The whole warp walks the loop converged and one ELECTED lane issues: a plain `if (lane == 0)` makes the
-        // issue code thread-divergent and ptxas wraps every TMA / MMA in ELECT + R2UR.BROADCAST + BRA.U.ANY sequences
-        // (measured: ~550 cycles of issue latency per k-block, the kernel's bottleneck in profiles/r01_*conv320*).
-        {
-            int stage = 0;
-            uint32_t phase = 0;
-            int cur_nt = -1;
-            uint32_t bphase = 0;
-            int ti = 0;
-            for (int wi = unit; wi < total_tiles; wi += n_units, ++ti) {
-                TC_DECODE_WORK(wi)
-                TC_DECODE_TILE(tile)
-                const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
-                if (lane == 0) { TC_TRACE(0, ti) }
-                if (p.b_resident && nt != cur_nt) {
-                    // (re)load the weight N-tile: skinny GEMMs (M >> N, short K) otherwise re-fetch it from L2 for every
-                    // M tile, which is more traffic than A itself and runs into the ~6300 B/clk chip-wide L2 cap
-                    tc::mbar_wait(bfree_bar, bphase ^ 1u);
-                    if (tc::elect_one()) {
-                        const uint32_t bytes = (uint32_t)main_kblocks * b_stage_bytes;
-                        if constexpr (kPair) {
-                            if (rank == 0) tc::mbar_arrive_expect_tx(bfull_bar, 2u * bytes);
-                            for (int kb = 0; kb < main_kblocks; ++kb)
-                                tc::tma_load_2d_pair(sB + (size_t)kb * b_stage_bytes, &p.tmB, bfull_bar, kb * kBlockK,
-                                                     nt * BN + (int)rank * b_rows);
-                        } else {
-                            tc::mbar_arrive_expect_tx(bfull_bar, bytes);
-                            for (int kb = 0; kb < main_kblocks; ++kb)
-                                tc::tma_load_2d(sB + (size_t)kb * b_stage_bytes, &p.tmB, bfull_bar, kb * kBlockK, nt * BN);
-                        }
-                    }
-                    __syncwarp();
-                    cur_nt = nt;
-                    bphase ^= 1u;
-                }
-                for (int kb = kb_begin; kb < kb_end; ++kb) {
-                    const int tap = fdiv(kb, p.fd_kc);
-                    const int kc = kb - tap * p.kc_per_tap;
-                    const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap], an = n0 + p.tap_dn[tap];
-                    {
-                        tc::mbar_wait(&empty_bar[stage], phase ^ 1u);
-                        if (tc::elect_one()) {
-                            uint8_t* dA = sA + (size_t)stage * kAStageBytes;
-                            uint8_t* dB = sB + (size_t)stage * b_stage_bytes;
-                            const int kcol = (tap * p.kc_per_tap + kc) * kBlockK;
-                            const uint32_t bytes = p.a_bytes + (p.b_resident ? 0u : b_stage_bytes);
-                            if constexpr (kPair) {
-                                // both CTAs' bytes are credited to the leader's barrier
-                                if (rank == 0) tc::mbar_arrive_expect_tx(&full_bar[stage], 2u * bytes);
-                                tc::tma_load_4d_pair(dA, &p.tmA, &full_bar[stage], kc * kBlockK, ax, ay, an);
-                                if (!p.b_resident)
-                                    tc::tma_load_2d_pair(dB, &p.tmB, &full_bar[stage], kcol, nt * BN + (int)rank * b_rows);
-                            } else {
-                                tc::mbar_arrive_expect_tx(&full_bar[stage], bytes);
-                                tc::tma_load_4d(dA, &p.tmA, &full_bar[stage], kc * kBlockK, ax, ay, an);
-                                if (!p.b_resident) tc::tma_load_2d(dB, &p.tmB, &full_bar[stage], kcol, nt * BN);
-                            }
-                        }
-                        __syncwarp();
-                        if (++stage == S) {
-                            stage = 0;
-                            phase ^= 1u;
-                        }
-                    }
-                }
-                // residual as extra k-blocks: acc[:, 64r:64r+64] += R[tile rows][64r:64r+64] @ I64  (TMA-coalesced, fully
-                // async; loading it from registers in the epilogue cost 32 us of a 81 us launch at M=81920, N=K=320)
-                for (int r = 0; r < res_kb; ++r) {
-                    tc::mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    if (tc::elect_one()) {
-                        uint8_t* dA = sA + (size_t)stage * kAStageBytes;   // A slot only: B is the resident identity
-                        if constexpr (kPair) {
-                            if (rank == 0) tc::mbar_arrive_expect_tx(&full_bar[stage], 2u * p.a_bytes);
-                            tc::tma_load_4d_pair(dA, &p.tmR, &full_bar[stage], nt * BN + r * kBlockK, x0, y0, n0);
-                        } else {
-                            tc::mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes);
-                            tc::tma_load_4d(dA, &p.tmR, &full_bar[stage], nt * BN + r * kBlockK, x0, y0, n0);
-                        }
-                    }
-                    __syncwarp();
-                    if (++stage == S) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
-                }
-                if (lane == 0) { TC_TRACE(1, ti) }
-            }
-        }
-#endif
-#if !defined(TC_GEMM_ISSUE_LEGACY)
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         // ONE elected lane runs the whole loop (waits included): issuing is the bottleneck of the narrow tiles — a k-block of
@@ -486,8 +395,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     tc::tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
                     TC_TRACE(2, ti)
-                    int pend = -1;
-                    (void)pend;
                     for (int kb = 0; kb < n_main; ++kb) {
                         tc::mbar_wait(&full_bar[stage], phase);
                         tc::tc_fence_after();
@@ -502,18 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                             else
                                 tc::umma_f16(d_tmem, mk(a_lo + 2u * k, a_hi), mk(b_lo + 2u * k, b_hi), idesc, (kb | k) != 0 ? 1u : 0u);
                         }
-#if defined(TC_GEMM_COMMIT2)
-                        // (experiment) release operand stages two k-blocks at a time: two back-to-back commits per pair
-                        if ((kb & 1) || kb == n_main - 1) {
-                            if (pend >= 0) { if constexpr (kPair) tc::umma_commit_pair(&empty_bar[pend]); else tc::umma_commit(&empty_bar[pend]); }
-                            if constexpr (kPair) tc::umma_commit_pair(&empty_bar[stage]); else tc::umma_commit(&empty_bar[stage]);
-                            pend = -1;
-                        } else {
-                            pend = stage;
-                        }
-#else
                         if constexpr (kPair) tc::umma_commit_pair(&empty_bar[stage]); else tc::umma_commit(&empty_bar[stage]);
-#endif
                         if (++stage == S) {
                             stage = 0;
                             phase ^= 1u;
@@ -551,79 +447,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             }
             __syncwarp();
         }
-#else
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (rank == 0) {
-            const uint32_t idesc = tc::umma_idesc_f16(kPair ? 2 * kBlockM : kBlockM, (uint32_t)BN, 0, 0);
-            const uint64_t a_desc0 = tc::umma_desc_sw128(tc::smem_u32(sA));
-            const uint64_t b_desc0 = tc::umma_desc_sw128(tc::smem_u32(sB));
-            const uint64_t eye_desc = tc::umma_desc_sw128(tc::smem_u32(s_eye));
-            const uint32_t idesc_eye = tc::umma_idesc_f16(kPair ? 2 * kBlockM : kBlockM, 64u, 0, 0);
-            const uint64_t a_step = (uint64_t)(kAStageBytes >> 4), b_step = (uint64_t)(b_stage_bytes >> 4);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            int cur_nt = -1;
-            uint32_t bphase = 0;
-            int ti = 0;
-            for (int wi = unit; wi < total_tiles; wi += n_units, ++ti) {
-                TC_DECODE_WORK(wi)
-                const int n_main = kb_end - kb_begin;
-                const int kblocks = n_main + res_kb;      // k-blocks of this work item (residual ones last)
-                if (p.b_resident && TC_TILE_NT(tile) != cur_nt) {
-                    tc::mbar_wait(bfull_bar, bphase);
-                    bphase ^= 1u;
-                    cur_nt = TC_TILE_NT(tile);
-                }
-                tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
-                tc::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
-                if (lane == 0) { TC_TRACE(2, ti) }
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    tc::mbar_wait(&full_bar[stage], phase);
-                    tc::tc_fence_after();
-                    if (kb == 0 && lane == 0) { TC_TRACE(3, ti) }
-                    if (tc::elect_one()) {
-                        const int r = kb - n_main;           // >= 0: residual k-block, N = 64 onto columns [64 r, 64 r + 64)
-                        const uint64_t a_desc = a_desc0 + a_step * (uint64_t)stage;
-                        const uint64_t b_desc = r >= 0 ? eye_desc : b_desc0 + b_step * (uint64_t)(p.b_resident ? kb : stage);
-                        const uint32_t id = r >= 0 ? idesc_eye : idesc;
-                        const uint32_t dcol = d_tmem + (r >= 0 ? (uint32_t)(r * 64) : 0u);
-#pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k) {
-                            // advance 16 halfs = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
-                            if constexpr (kPair)
-                                tc::umma_f16_pair(dcol, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), id,
-                                                  (kb | k) != 0 ? 1u : 0u);
-                            else
-                                tc::umma_f16(dcol, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), id,
-                                             (kb | k) != 0 ? 1u : 0u);
-                        }
-                        if constexpr (kPair) tc::umma_commit_pair(&empty_bar[stage]); else tc::umma_commit(&empty_bar[stage]);
-                    }
-                    __syncwarp();
-                    if (++stage == S) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
-                }
-                if (tc::elect_one()) {
-                    if constexpr (kPair) tc::umma_commit_pair(&tfull_bar[acc]); else tc::umma_commit(&tfull_bar[acc]);
-                    // last tile on this weight N-tile: tell the producer(s) when its MMAs have drained
-                    const int next = wi + n_units;        // (weights are only resident without split-K: work item == tile)
-                    if (p.b_resident && next < total_tiles && TC_TILE_NT(next) != cur_nt) {
-                        if constexpr (kPair) tc::umma_commit_pair(bfree_bar); else tc::umma_commit(bfree_bar);
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) { TC_TRACE(4, ti) }
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
-            }
-        }
-#endif
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..9)
         // Two warps per TMEM lane quadrant: "column group" 0 takes the first half of the tile's columns, group 1 the
