@@ -42,14 +42,14 @@ def variants():
         for p in (1, 2, 3, 4):
             yield f"v3 poly={p}/8", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY=str(p))
     yield "v3 p0", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY="0")
-    yield "v3 p1", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY="1")
+    yield "v3 single", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY="0", TC_ATTN_SINGLE="1")
     if os.environ.get("ATTN_AB_ALL") == "1":
         yield "v3 p0 token", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY="0", TC_ATTN_PP="1")
         yield "v3 p0 stagger", dict(TC_ATTN_IMPL="v3", TC_ATTN_POLY="0", TC_ATTN_STAGGER="1200")
 
 
 def set_env(e):
-    for k in ("TC_ATTN_IMPL", "TC_ATTN_POLY", "TC_ATTN_PP", "TC_ATTN_STAGGER"):
+    for k in ("TC_ATTN_IMPL", "TC_ATTN_POLY", "TC_ATTN_PP", "TC_ATTN_STAGGER", "TC_ATTN_SINGLE"):
         os.environ.pop(k, None)
     os.environ.update(e)
 

@@ -37,6 +37,7 @@ struct alignas(64) Attn3Params {
     float scale_log2;
     int pingpong;   // the two query tiles take turns on the exponential phase (named-barrier token), see the softmax loops
     int stagger;    // cycles by which query tile 1 starts late (keeps the two tiles' exponential phases out of step)
+    int single;     // one query tile per CTA (192 threads, 256 TMEM columns, two K/V stages): two independent CTAs per SM
 };
 
 typedef unsigned long long u64;
@@ -132,15 +133,15 @@ struct AttnBars {
     uint64_t *bar_q, *k_full, *k_free, *v_full, *v_free, *s_full, *s_free, *p_ready, *o_full;
 };
 __device__ __forceinline__ void attn_issue_tile(const Attn3Params& p, const AttnBars& b, int w, int G, uint32_t tmem_base, uint32_t sQ_a,
-                                                uint32_t sK_a, uint32_t sV_a) {
+                                                uint32_t sK_a, uint32_t sV_a, int nst, uint32_t tm_o, uint32_t tm_p) {
     auto block_nk = [&](int g) {
         const int left = p.Lk - g * kKVTile;
         return left < kKVTile ? ((left + 15) & ~15) : kKVTile;
     };
     const uint64_t qd = tc::umma_desc_sw128(sQ_a + (uint32_t)w * kTileBytes);
     const uint64_t kd0 = tc::umma_desc_sw128(sK_a);
-    const uint32_t s_tmem = tmem_base + (uint32_t)w * 128, o_tmem = tmem_base + kTmemO + (uint32_t)w * 64,
-                   p_tmem = tmem_base + kTmemP + (uint32_t)w * 64;
+    const uint32_t s_tmem = tmem_base + (uint32_t)w * 128, o_tmem = tmem_base + tm_o + (uint32_t)w * 64,
+                   p_tmem = tmem_base + tm_p + (uint32_t)w * 64;
     auto issue_s = [&](int st, int nk) {          // called by ONE elected lane
         const uint32_t idesc = tc::umma_idesc_f16(128, (uint32_t)nk, 0, 0);
         const uint64_t kd = kd0 + (uint64_t)(st * (kTileBytes >> 4));
@@ -163,8 +164,8 @@ __device__ __forceinline__ void attn_issue_tile(const Attn3Params& p, const Attn
         for (int g = 0; g < G; ++g) {
             const int nk = block_nk(g);
             if (g + 1 < G) {
-                const int st1 = (st + 1 == kStages) ? 0 : st + 1;
-                const uint32_t ph1 = (st + 1 == kStages) ? (ph ^ 1u) : ph;
+                const int st1 = (st + 1 == nst) ? 0 : st + 1;
+                const uint32_t ph1 = (st + 1 == nst) ? (ph ^ 1u) : ph;
                 tc::mbar_wait(&b.k_full[st1], ph1);
                 tc::mbar_wait(&b.s_free[w], (uint32_t)(g & 1));
                 tc::tc_fence_after();
@@ -186,7 +187,7 @@ __device__ __forceinline__ void attn_issue_tile(const Attn3Params& p, const Attn
             }
             tc::umma_commit(&b.o_full[w]);
             tc::umma_commit(&b.v_free[st]);
-            if (++st == kStages) { st = 0; ph ^= 1u; }
+            if (++st == nst) { st = 0; ph ^= 1u; }
         }
     }
     __syncwarp();
@@ -198,10 +199,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_cons
     tc::pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                  // 2 tiles
-    uint8_t* sK = smem + 2 * kTileBytes;                 // kStages
-    uint8_t* sV = smem + (2 + kStages) * kTileBytes;     // kStages
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + 2 * kStages) * kTileBytes);
+    // single mode: ONE query tile per CTA, 192 threads, 256 TMEM columns, two K/V stages — two such CTAs share an SM and run
+    // out of step by themselves (independent barriers), so one CTA's exponentials overlap the other's TMEM / PV round trip
+    const bool single = p.single != 0;
+    const int nq = single ? 1 : 2, nst = single ? 2 : kStages;
+    const uint32_t tm_o = single ? 128u : kTmemO, tm_p = single ? 192u : kTmemP, tm_cols = single ? 256u : kTmemCols;
+    const int warp_mma0 = single ? 4 : 8, warp_tma = single ? 5 : 9, warp_mma1 = single ? -1 : 10, n_soft = single ? 4 : 8;
+    uint8_t* sQ = smem;                                  // nq tiles
+    uint8_t* sK = smem + nq * kTileBytes;                // nst stages
+    uint8_t* sV = sK + nst * kTileBytes;                 // nst stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + nst * kTileBytes);
     uint64_t* bar_q = bars + 0;
     uint64_t* k_full = bars + 1;                 // [kStages]
     uint64_t* k_free = k_full + kStages;
@@ -216,10 +223,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_cons
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
-    const int q0 = blockIdx.x * 2 * kQTile;
+    const int q0 = blockIdx.x * nq * kQTile;
     const int head = blockIdx.y;
     const int qb = blockIdx.z;
-    const int ntiles = (q0 + kQTile < p.Lq) ? 2 : 1;
+    const int ntiles = (!single && q0 + kQTile < p.Lq) ? 2 : 1;
     const int G = (p.Lk + kKVTile - 1) / kKVTile;
 
     if (tid == 0) {
@@ -239,8 +246,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_cons
         }
         tc::fence_mbar_init();
     }
-    if (warp == 8) {
-        tc::tmem_alloc(tmem_ptr_smem, kTmemCols);
+    if (warp == warp_mma0) {
+        tc::tmem_alloc(tmem_ptr_smem, tm_cols);
         tc::tmem_relinquish();
     }
     tc::tc_fence_before();
@@ -249,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_cons
     const uint32_t tmem_base = *tmem_ptr_smem;
     tc::pdl_wait();   // prologue (barriers, TMEM) overlapped the predecessor; Q/K/V are its results
 
-    if (warp == 9) {
+    if (warp == warp_tma) {
         // ------------------------------------------------------------------------------ TMA producer
         if (tc::elect_one()) {
             tc::tma_prefetch_desc(&p.tmQ);
@@ -275,23 +282,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_cons
                 tc::tma_load_3d(sV + st * kTileBytes, &p.tmV, &v_full[st], head * 64, g * kKVTile, kvb);
             }
             __syncwarp();
-            if (++st == kStages) { st = 0; ph ^= 1u; }
+            if (++st == nst) { st = 0; ph ^= 1u; }
         }
-    } else if (warp == 8 || warp == 10) {
+    } else if (warp == warp_mma0 || warp == warp_mma1) {
         // ------------------------------------------------------------------------------ MMA issuers (one per query tile)
-        const int w = warp == 8 ? 0 : 1;
+        const int w = warp == warp_mma0 ? 0 : 1;
         if (w < ntiles) {
             const AttnBars b{bar_q, k_full, k_free, v_full, v_free, s_full, s_free, p_ready, o_full};
-            attn_issue_tile(p, b, w, G, tmem_base, tc::smem_u32(sQ), tc::smem_u32(sK), tc::smem_u32(sV));
+            attn_issue_tile(p, b, w, G, tmem_base, tc::smem_u32(sQ), tc::smem_u32(sK), tc::smem_u32(sV), nst, tm_o, tm_p);
         }
-    } else if (warp < 8 && (warp >> 2) < ntiles) {
+    } else if (warp < n_soft && (warp >> 2) < ntiles) {
         // ------------------------------------------------------------------------------ softmax warpgroups
         const int w = warp >> 2;
         const int row = tid & 127;
         const uint32_t lane_off = ((uint32_t)((warp & 3) * 32)) << 16;
         const uint32_t tmem_s = tmem_base + (uint32_t)w * 128 + lane_off;
-        const uint32_t tmem_o = tmem_base + kTmemO + (uint32_t)w * 64 + lane_off;
-        const uint32_t tmem_p = tmem_base + kTmemP + (uint32_t)w * 64 + lane_off;
+        const uint32_t tmem_o = tmem_base + tm_o + (uint32_t)w * 64 + lane_off;
+        const uint32_t tmem_p = tmem_base + tm_p + (uint32_t)w * 64 + lane_off;
         const float c = p.scale_log2;
         const u64 c2 = pack2(c, c);
         float m_run = -INFINITY, l_run = 0.f;
@@ -438,9 +445,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_attn3_kernel(const __grid_cons
 
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == warp_mma0) {
         tc::tc_fence_after();
-        tc::tmem_dealloc(tmem_base, kTmemCols);
+        tc::tmem_dealloc(tmem_base, tm_cols);
     }
 }
 
@@ -449,12 +456,12 @@ int launch_attn3(const Attn3Params& p, dim3 grid, size_t smem_bytes, cudaStream_
     static bool attr_set = false;
     if (!attr_set) {
         int rc = tc_host::check_cuda(cudaFuncSetAttribute(tc_attn3_kernel<kPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                          (int)smem_bytes),
+                                                          (int)((size_t)(2 + 2 * kStages) * kTileBytes + 1024 + 512 + 4096)),
                                      "cudaFuncSetAttribute(tc_attn3_kernel)");
         if (rc) return rc;
         attr_set = true;
     }
-    tc_host::launch(tc_attn3_kernel<kPoly>, grid, dim3(kThreads), smem_bytes, stream, 1, p);
+    tc_host::launch(tc_attn3_kernel<kPoly>, grid, dim3(p.single ? 192 : kThreads), smem_bytes, stream, 1, p);
     return 0;
 }
 
@@ -769,8 +776,17 @@ int tc_attention_v3(const TcAttention* d, int poly_of_8, cudaStream_t stream) {
         const char* sg_env = getenv("TC_ATTN_STAGGER");   // cycles (A/B testing)
         p.stagger = sg_env ? atoi(sg_env) : 0;
     }
-    const size_t smem_bytes = (size_t)(2 + 2 * kStages) * kTileBytes + 1024 + 512 + 4096;
-    dim3 grid((d->Lq + 2 * kQTile - 1) / (2 * kQTile), d->heads, d->q_batches);
+    {
+        // one query tile per CTA (two independent CTAs per SM) for the UNet's self attentions: L = 2560 456 -> 423 us, L = 640
+        // 103 -> 85 us in one A/B call; the long-K/V fusion attention (20480 keys) is 4 % faster with two tiles per CTA
+        // sharing each K/V stage (profiles/r02_attn_single_ab.txt)
+        const char* sg = getenv("TC_ATTN_SINGLE");       // "0" / "1" force (A/B testing)
+        p.single = sg ? (sg[0] == '1') : (d->Lk[0] <= 4096);
+    }
+    const size_t smem_full = (size_t)(2 + 2 * kStages) * kTileBytes + 1024 + 512 + 4096;
+    const size_t smem_bytes = p.single ? (size_t)(1 + 2 * 2) * kTileBytes + 1024 + 512 + 1024 : smem_full;
+    const int rows_per_cta = p.single ? kQTile : 2 * kQTile;
+    dim3 grid((d->Lq + rows_per_cta - 1) / rows_per_cta, d->heads, d->q_batches);
     int rc;
     switch (poly_of_8) {
         case 0: rc = launch_attn3<0>(p, grid, smem_bytes, stream); break;
