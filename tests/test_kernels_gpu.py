@@ -332,6 +332,34 @@ def test_groupnorm(ops, frames, fps, hw, C, silu, eps):
     _close(y, ref, "groupnorm")
 
 
+@pytest.mark.parametrize("frames,fps,hw,C", [
+    (1, 1, 1021, 1280),      # single-pass kernel, one CTA per (statistics group, norm group), ragged vector count
+    (2, 1, 1501, 1280),      # cluster of 2 CTAs per unit
+    (1, 1, 5003, 1280),      # cluster of 5
+    (1, 1, 6000, 1280),      # cluster of 6 (15.4 MB: the largest tensor the single-pass path takes)
+    (4, 2, 333, 2560),       # 80-channel groups (ten 16-byte vectors per pixel)
+    (64, 1, 40, 512),        # many small units (2048 of them): fuller threads, small blocks
+    (2, 2, 1280, 256),       # 8-channel groups: one vector per pixel
+])
+def test_groupnorm_single_pass_cluster_shapes(ops, frames, fps, hw, C):
+    """Shapes that reach gn_fused_kernel with different cluster sizes (partial sums through distributed shared memory,
+    added in rank order): against torch, in place as well, and identical run to run."""
+    x = (_rand(frames, hw, C, seed=141) * 1.5 + 0.3).half()
+    gamma = (_rand(C, seed=142) * 0.2 + 1.0).float()
+    beta = (_rand(C, seed=143) * 0.2).float()
+    outs = []
+    for rep in range(2):
+        y = torch.zeros_like(x)
+        ops.groupnorm(x, y, gamma, beta, frames=frames, frames_per_stat=fps, hw=hw, C=C, silu=True)
+        outs.append(y)
+    z = x.clone()
+    ops.groupnorm(z, z, gamma, beta, frames=frames, frames_per_stat=fps, hw=hw, C=C, silu=True)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], z), "single-pass GroupNorm differs run to run / in place"
+    xr = x.float().reshape(frames // fps, fps * hw, C).permute(0, 2, 1)
+    ref = F.silu(F.group_norm(xr, 32, gamma, beta, 1e-5)).permute(0, 2, 1).reshape(frames, hw, C)
+    _close(outs[0], ref, f"single-pass groupnorm {frames}x{fps}x{hw}x{C}")
+
+
 @pytest.mark.parametrize("frames,fps,hw,C,slice_ld,inplace", [
     (32, 16, 2560, 320, 0, False),      # 52 MB, per-clip statistics
     (32, 1, 2560, 320, 0, True),        # per-frame statistics, in place
@@ -412,6 +440,22 @@ def test_attention_self(ops, B, L, heads):
     # P is rounded to fp16 for the PV product (as the reference's autocast bmm does); with few keys (L = 40) the
     # rounding is averaged less: measured <= 0.033 % of the outputs outside the literal tolerance
     _close(out, _sdpa_ref(q, k, v, heads), f"self attention L={L}", ns_max=1e-3)
+
+
+@pytest.mark.parametrize("single", ["0", "1"])
+@pytest.mark.parametrize("B,L,Lk,heads", [(2, 300, 300, 2), (1, 640, 640, 3), (2, 257, 1100, 1)])
+def test_attention_both_cta_modes(ops, monkeypatch, single, B, L, Lk, heads):
+    """tc_attn3_kernel with two query tiles per CTA (one CTA per SM) and with one tile per CTA (two CTAs per SM): the
+    dispatch picks by key count, TC_ATTN_SINGLE forces either — both must agree with the fp32 reference at every shape."""
+    monkeypatch.setenv("TC_ATTN_SINGLE", single)
+    C = heads * 64
+    q = _rand(B, L, C, seed=161).half()
+    k = _rand(B, Lk, C, seed=162).half()
+    v = _rand(B, Lk, C, seed=163).half()
+    out = torch.zeros_like(q)
+    ops.attention(q, [dict(k=k, v=v, ldk=C, ldv=C, Lk=Lk)], out, q_batches=B, Lq=L, heads=heads, scale=64 ** -0.5,
+                  ldq=C, ldo=C)
+    _close(out, _sdpa_ref(q, k, v, heads), f"attention L={L} Lk={Lk} single={single}", ns_max=1e-3)
 
 
 def test_attention_fused_qkv_layout(ops):

@@ -142,6 +142,9 @@ class DecoderEngine:
         """AttnBlock (autoencoder_dualref.py:172-206): GroupNorm -> fused q/k/v 1x1 convs -> one fused single-head attention
         kernel per call (head dim = C, scores never leave the SM) -> proj_out + residual."""
         N, H, W, C = x.N, x.H, x.W, p.C
+        if C % 64 or C > 512 or (C > 256 and C % 128):
+            raise NotImplementedError(f"mid-block attention: {C} channels (tc_attention_wide takes multiples of 64 up to 512, "
+                                      f"of 128 above 256)")
         n = bld.act(N, H, W, C)
         groupnorm(bld, x, n, p.norm)
         qkv = bld.act(N, H, W, 3 * C)
