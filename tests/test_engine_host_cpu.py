@@ -127,10 +127,18 @@ def test_programs_plan_for_other_geometries_with_valid_launch_arguments():
     deng = vae_engine.DecoderEngine(dec, device="meta", plan_only=True)
     for (T, h, w) in ((16, 40, 64), (14, 40, 64), (16, 72, 128)):
         plan = deng.plan_for(T, h, w)
-        for fn, a, kw in list(plan.ctx.calls) + list(plan.main.calls):
+        calls = list(plan.ctx.calls) + list(plan.main.calls)
+        for fn, a, kw in calls:
             if fn is ops.conv_gemm:
                 _check_conv_gemm_call(a, kw)
         assert plan.arena.high_water < (170 << 30)
+        # the mid-block AttnBlock (autoencoder_dualref.py:172-206) is ONE fused launch: head dim = its 512 channels, q / k / v
+        # channel slices of one projection output, no score matrix in memory (no softmax_rows, no per-frame score GEMMs)
+        wide = [(a, kw) for fn, a, kw in calls if fn is ops.attention_wide]
+        assert len(wide) == 1 and not any(fn is ops.softmax_rows for fn, a, kw in calls)
+        kw = wide[0][1]
+        assert kw["D"] == 512 and kw["batches"] == T and kw["L"] == h * w and kw["ld"] == 3 * 512 and kw["ldo"] == 512
+        assert (kw["q_offset"], kw["k_offset"], kw["v_offset"]) == (0, 512, 1024) and abs(kw["scale"] - 512 ** -0.5) < 1e-9
 
 
 def test_freshly_allocated_contexts_are_never_served_from_a_stale_cache():
